@@ -1,0 +1,344 @@
+// BN254 Fr / Fq Montgomery arithmetic on 8 x 32-bit limbs for sm_100a.
+//
+// Replaces (on the device) halo2curves 0.3.1 `bn256::Fr` / `bn256::Fq`
+// ([DEP] halo2curves/src/bn256/{fr,fq}.rs, pinned at reference Cargo.lock:484-486):
+// same Montgomery radix R = 2^256, so the 4 x u64 little-endian limbs the Rust side
+// holds are reinterpreted as 8 x u32 with no conversion.
+//
+// Multiplication is a CIOS Montgomery product split into an "even" and an "odd"
+// accumulator so that every partial product is one 64-bit multiply-accumulate
+// (mad.lo.cc + madc.hi.cc, which ptxas fuses into IMAD.WIDE.U32 with carry) and no
+// carry ever has to ripple between misaligned columns.  After each row the implicit
+// division by 2^32 swaps the roles of the two accumulators; with the loops fully
+// unrolled the swap and the two-limb shift are pure register renaming.
+//
+// Every function is __host__ __device__: the host bodies are a plain-C emulation of
+// the same limb schedule so the algorithm is unit-tested on the CPU (tests/
+// test_field_host.py) before any GPU time is spent.  The host bodies are test-only;
+// the product never calls them.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ZK_HD __host__ __device__ __forceinline__
+#define ZK_D __device__ __forceinline__
+#else
+#define ZK_HD inline
+#define ZK_D inline
+#endif
+
+namespace zk {
+
+// ------------------------------------------------------------------ field parameters
+struct FrParams {
+    // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+    // (reference solidity_verifier_contract/contract.sol:211)
+    static constexpr uint32_t P0 = 0xf0000001u, P1 = 0x43e1f593u, P2 = 0x79b97091u, P3 = 0x2833e848u,
+                              P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+    static constexpr uint32_t INV = 0xefffffffu;  // -r^{-1} mod 2^32
+    // R mod r
+    static constexpr uint32_t ONE0 = 0x4ffffffbu, ONE1 = 0xac96341cu, ONE2 = 0x9f60cd29u, ONE3 = 0x36fc7695u,
+                              ONE4 = 0x7879462eu, ONE5 = 0x666ea36fu, ONE6 = 0x9a07df2fu, ONE7 = 0x0e0a77c1u;
+    // R^2 mod r
+    static constexpr uint32_t RR0 = 0xae216da7u, RR1 = 0x1bb8e645u, RR2 = 0xe35c59e3u, RR3 = 0x53fe3ab1u,
+                              RR4 = 0x53bb8085u, RR5 = 0x8c49833du, RR6 = 0x7f4e44a5u, RR7 = 0x0216d0b1u;
+};
+
+struct FqParams {
+    // q = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+    // (reference solidity_verifier_contract/contract.sol:210)
+    static constexpr uint32_t P0 = 0xd87cfd47u, P1 = 0x3c208c16u, P2 = 0x6871ca8du, P3 = 0x97816a91u,
+                              P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+    static constexpr uint32_t INV = 0xe4866389u;
+    static constexpr uint32_t ONE0 = 0xc58f0d9du, ONE1 = 0xd35d438du, ONE2 = 0xf5c70b3du, ONE3 = 0x0a78eb28u,
+                              ONE4 = 0x7879462cu, ONE5 = 0x666ea36fu, ONE6 = 0x9a07df2fu, ONE7 = 0x0e0a77c1u;
+    static constexpr uint32_t RR0 = 0x538afa89u, RR1 = 0xf32cfc5bu, RR2 = 0xd44501fbu, RR3 = 0xb5e71911u,
+                              RR4 = 0x0a417ff6u, RR5 = 0x47ab1effu, RR6 = 0xcab8351fu, RR7 = 0x06d89f71u;
+};
+
+// -------------------------------------------------------------- limb-chain primitives
+// acc(8 limbs) += sum_t x[t] * y * 2^(64 t), t = 0..3; returns the carry out of limb 7.
+// `cin` (0/1) is added at limb 0.
+ZK_HD uint32_t mad_row4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+#ifdef __CUDA_ARCH__
+    uint32_t c;
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "=r"(c)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+    return c;
+#else
+    const uint32_t x[4] = {x0, x1, x2, x3};
+    uint64_t carry = 0;
+    for (int t = 0; t < 4; ++t) {
+        unsigned __int128 s = (unsigned __int128)x[t] * y + (((uint64_t)acc[2 * t + 1] << 32) | acc[2 * t]) + carry;
+        acc[2 * t] = (uint32_t)s;
+        acc[2 * t + 1] = (uint32_t)(s >> 32);
+        carry = (uint64_t)(s >> 64);
+    }
+    return (uint32_t)carry;
+#endif
+}
+
+// lo += stray (one limb); the carry of that add enters the chain acc += x*y as above.
+// No carry can leave limb 7 here (see the bound argument in mont_mul).
+ZK_HD void mad_row4_stray(uint32_t& lo, uint32_t stray, uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2,
+                          uint32_t x3, uint32_t y) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "madc.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.u32 %7, %13, %14, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "+r"(lo)
+        : "r"(stray), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+#else
+    uint64_t s0 = (uint64_t)lo + stray;
+    lo = (uint32_t)s0;
+    const uint32_t x[4] = {x0, x1, x2, x3};
+    uint64_t carry = s0 >> 32;
+    for (int t = 0; t < 4; ++t) {
+        unsigned __int128 s = (unsigned __int128)x[t] * y + (((uint64_t)acc[2 * t + 1] << 32) | acc[2 * t]) + carry;
+        acc[2 * t] = (uint32_t)s;
+        acc[2 * t + 1] = (uint32_t)(s >> 32);
+        carry = (uint64_t)(s >> 64);
+    }
+#endif
+}
+
+ZK_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+
+// r = a + b (8 limbs), returns carry
+ZK_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#ifdef __CUDA_ARCH__
+    uint32_t c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint64_t s = (uint64_t)a[i] + b[i] + c;
+        r[i] = (uint32_t)s;
+        c = s >> 32;
+    }
+    return (uint32_t)c;
+#endif
+}
+
+// r = a - b (8 limbs), returns borrow (1 if a < b)
+ZK_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#ifdef __CUDA_ARCH__
+    uint32_t c;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c & 1u;  // subc.u32 0-0-borrow = 0xffffffff when borrow
+#else
+    int64_t c = 0;
+    for (int i = 0; i < 8; ++i) {
+        int64_t s = (int64_t)a[i] - b[i] - c;
+        r[i] = (uint32_t)s;
+        c = (s < 0) ? 1 : 0;
+    }
+    return (uint32_t)c;
+#endif
+}
+
+// ------------------------------------------------------------------------ the field
+template <class P>
+struct alignas(16) Fp {
+    uint32_t l[8];
+
+    static ZK_HD void modulus(uint32_t* m) {
+        m[0] = P::P0; m[1] = P::P1; m[2] = P::P2; m[3] = P::P3;
+        m[4] = P::P4; m[5] = P::P5; m[6] = P::P6; m[7] = P::P7;
+    }
+    static ZK_HD Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = 0;
+        return r;
+    }
+    static ZK_HD Fp one() {  // Montgomery form of 1
+        Fp r;
+        r.l[0] = P::ONE0; r.l[1] = P::ONE1; r.l[2] = P::ONE2; r.l[3] = P::ONE3;
+        r.l[4] = P::ONE4; r.l[5] = P::ONE5; r.l[6] = P::ONE6; r.l[7] = P::ONE7;
+        return r;
+    }
+    static ZK_HD Fp r2() {
+        Fp r;
+        r.l[0] = P::RR0; r.l[1] = P::RR1; r.l[2] = P::RR2; r.l[3] = P::RR3;
+        r.l[4] = P::RR4; r.l[5] = P::RR5; r.l[6] = P::RR6; r.l[7] = P::RR7;
+        return r;
+    }
+
+    ZK_HD bool is_zero() const {
+        return (l[0] | l[1] | l[2] | l[3] | l[4] | l[5] | l[6] | l[7]) == 0;
+    }
+    ZK_HD bool operator==(const Fp& o) const {
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d |= l[i] ^ o.l[i];
+        return d == 0;
+    }
+    ZK_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+
+    // value in [0, 2p) -> [0, p)
+    ZK_HD void reduce_once() {
+        uint32_t m[8], t[8];
+        modulus(m);
+        uint32_t borrow = sub8(t, l, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) l[i] = borrow ? l[i] : t[i];
+    }
+
+    friend ZK_HD Fp operator+(const Fp& a, const Fp& b) {
+        Fp r;
+        add8(r.l, a.l, b.l);  // a + b < 2p < 2^255: no carry
+        r.reduce_once();
+        return r;
+    }
+    friend ZK_HD Fp operator-(const Fp& a, const Fp& b) {
+        Fp r;
+        uint32_t m[8], t[8];
+        modulus(m);
+        uint32_t borrow = sub8(r.l, a.l, b.l);
+        add8(t, r.l, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = borrow ? t[i] : r.l[i];
+        return r;
+    }
+    ZK_HD Fp neg() const {
+        Fp r;
+        uint32_t m[8];
+        modulus(m);
+        sub8(r.l, m, l);
+        bool z = is_zero();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = z ? 0u : r.l[i];
+        return r;
+    }
+    ZK_HD Fp dbl() const { return *this + *this; }
+
+    // Montgomery product a*b*2^-256 mod p, inputs and output fully reduced.
+    //
+    // T = E + 2^32 * O (+ one stray limb carried between rows).  Row i adds a*b_i and
+    // m*p with m chosen so the low limb cancels; V = T + a*b_i + m*p < 2^288, hence
+    // O (weight 2^32) never overflows 8 limbs and E needs one carry limb E[8].
+    // Dividing by 2^32 turns O into the next row's even accumulator unchanged, E[2..8]
+    // into the next odd accumulator, and leaves E[1] as a stray limb of weight 1 that
+    // is added to the new E[0], its carry entering the new O chain (same weight 2^32).
+    friend ZK_HD Fp operator*(const Fp& a, const Fp& b) {
+        uint32_t m[8];
+        modulus(m);
+        uint32_t stray = 0;
+        uint32_t E[9], O[9];  // E[8] is the carry limb of the even accumulator
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t bi = b.l[i];
+            mad_row4_stray(E[0], stray, O, a.l[1], a.l[3], a.l[5], a.l[7], bi);
+            E[8] += mad_row4(E, a.l[0], a.l[2], a.l[4], a.l[6], bi);
+            const uint32_t mi = mul_lo(E[0], P::INV);
+            E[8] += mad_row4(E, m[0], m[2], m[4], m[6], mi);
+            mad_row4(O, m[1], m[3], m[5], m[7], mi);
+            // divide by 2^32: rename
+            stray = E[1];
+            uint32_t nO[9];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) nO[j] = E[j + 2];
+            nO[7] = 0; nO[8] = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) E[j] = O[j];
+            E[8] = 0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) O[j] = nO[j];
+        }
+        // merge: T = E + stray + 2^32 * O   (T < 2p < 2^255)
+        Fp r;
+        uint32_t s[8], o[8];
+        s[0] = stray;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) s[j] = O[j - 1];
+        add8(o, E, s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r.l[j] = o[j];
+        r.reduce_once();
+        return r;
+    }
+    ZK_HD Fp sqr() const { return (*this) * (*this); }
+
+    // canonical integer -> Montgomery, and back
+    ZK_HD Fp to_mont() const { return (*this) * r2(); }
+    ZK_HD Fp from_mont() const {
+        Fp o = zero();
+        o.l[0] = 1;
+        return (*this) * o;
+    }
+
+    // a^e for a 256-bit exponent given as 8 limbs (variable time)
+    ZK_HD Fp pow(const uint32_t* e) const {
+        Fp r = one();
+        for (int i = 255; i >= 0; --i) {
+            r = r.sqr();
+            if ((e[i >> 5] >> (i & 31)) & 1u) r = r * (*this);
+        }
+        return r;
+    }
+    ZK_HD Fp pow_u64(uint64_t e) const {
+        Fp r = one();
+        Fp b = *this;
+        while (e) {
+            if (e & 1) r = r * b;
+            b = b.sqr();
+            e >>= 1;
+        }
+        return r;
+    }
+    // Fermat inverse (0 -> 0)
+    ZK_HD Fp inverse() const {
+        uint32_t e[8];
+        modulus(e);
+        e[0] -= 2;  // p - 2; low limb of both moduli is >= 2
+        return pow(e);
+    }
+};
+
+using Fr = Fp<FrParams>;
+using Fq = Fp<FqParams>;
+
+}  // namespace zk
