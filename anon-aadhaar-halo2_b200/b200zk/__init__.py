@@ -1,0 +1,26 @@
+"""b200zk — host-side mirror of the halo2_proofs hot-path interface over the C ABI.
+
+Names, argument meaning and error behaviour follow the upstream Rust items the C ABI
+replaces ([DEP] halo2_proofs 0.2.0 @ v2023_01_20, reference Cargo.lock:469-471):
+
+    arithmetic::best_fft            -> best_fft(a, omega, log_n)
+    arithmetic::best_multiexp       -> best_multiexp(coeffs, bases)
+    poly::EvaluationDomain          -> EvaluationDomain(j, k).{lagrange_to_coeff, ...}
+    poly::kzg::commitment::ParamsKZG -> ParamsKZG(g, g_lagrange).{commit, commit_lagrange}
+
+Arrays are numpy ``uint64`` in the wire layout of halo2curves (4 LE limbs, Montgomery):
+Fr vectors are (n, 4), G1Affine vectors (n, 8), a G1 result (12,).  Like upstream, bad
+lengths are programming errors: they raise ``AssertionError`` (Rust ``assert_eq!``).
+"""
+from ._lib import B200zkError, LIB_PATH, header_symbols, load, check  # noqa: F401
+from .api import (  # noqa: F401
+    EvaluationDomain,
+    ParamsKZG,
+    best_fft,
+    best_multiexp,
+    g1_sum,
+    init,
+    kernel_launches,
+    modmul_peak,
+    shutdown,
+)

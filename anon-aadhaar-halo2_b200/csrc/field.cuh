@@ -14,8 +14,9 @@
 //
 // Every function is __host__ __device__: the host bodies are a plain-C emulation of
 // the same limb schedule so the algorithm is unit-tested on the CPU (tests/
-// test_field_host.py) before any GPU time is spent.  The host bodies are test-only;
-// the product never calls them.
+// test_field_host.py) before any GPU time is spent.  In the product the host bodies
+// only ever prepare per-call scalar kernel parameters (e.g. zeta^2 or n^-1 * zeta);
+// array data is never processed on the host.
 #pragma once
 #include <stdint.h>
 

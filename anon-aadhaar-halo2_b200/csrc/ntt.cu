@@ -1,0 +1,414 @@
+// Host driver + C ABI for the Fr NTT kernels (see ntt.cuh for the algorithm and the
+// upstream functions being replaced).
+#include "../../include/b200zk.h"
+#include "common.cuh"
+#include "ntt.cuh"
+
+#include <cstring>
+
+namespace zk {
+
+// out[i] = base^(i * mult)   (exponent < 2^32)
+static __global__ void fr_pow_table_kernel(Fr base, uint32_t mult, uint32_t count, Fr* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    st_fr(out + i, base.pow_u64((uint64_t)i * mult));
+}
+
+// Per-(omega, log_n) twiddle tables, built on the device once and cached.
+struct NttTables {
+    Fr omega;
+    uint32_t log_n;
+    int npass;
+    int bits[4];
+    Fr* tw_tile[NTT_MAX_B + 1];  // indexed by b
+    Fr* tw_lo;
+    Fr* tw_hi;
+    uint32_t tw_h;
+    Fr w8[3];
+    Fr* block;  // single allocation
+};
+
+static void plan_bits(uint32_t log_n, int& npass, int* bits) {
+    npass = (int)((log_n + NTT_MAX_B - 1) / NTT_MAX_B);
+    if (npass == 0) npass = 1;
+    int base = log_n / npass, rem = log_n % npass;
+    for (int p = 0; p < npass; ++p) bits[p] = base + (p < rem ? 1 : 0);
+}
+
+static NttTables* get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStream_t s) {
+    for (NttTables* t : c.ntt_tables)
+        if (t->log_n == log_n && t->omega == omega) return t;
+    ZK_REQUIRE(log_n >= 1 && log_n <= 28, "log_n out of range (1..28)");
+    NttTables* t = new NttTables();
+    t->omega = omega;
+    t->log_n = log_n;
+    plan_bits(log_n, t->npass, t->bits);
+    t->tw_h = (log_n + 1) / 2;
+    const size_t n_lo = (size_t)1 << t->tw_h, n_hi = (size_t)1 << (log_n - t->tw_h);
+    size_t total = n_lo + n_hi + 4;
+    bool need[NTT_MAX_B + 1] = {};
+    for (int p = 0; p < t->npass; ++p) need[t->bits[p]] = true;
+    for (int b = 1; b <= NTT_MAX_B; ++b)
+        if (need[b]) total += (size_t)1 << b;
+    ZK_CUDA(cudaMalloc(&t->block, total * sizeof(Fr)));
+    Fr* cur = t->block;
+    auto fill = [&](Fr* dst, uint32_t mult, uint32_t count) {
+        fr_pow_table_kernel<<<(count + 127) / 128, 128, 0, s>>>(omega, mult, count, dst);
+        ZK_LAUNCH_CHECK();
+    };
+    t->tw_lo = cur; cur += n_lo;
+    fill(t->tw_lo, 1, (uint32_t)n_lo);
+    t->tw_hi = cur; cur += n_hi;
+    fill(t->tw_hi, 1u << t->tw_h, (uint32_t)n_hi);
+    for (int b = 1; b <= NTT_MAX_B; ++b) {
+        t->tw_tile[b] = nullptr;
+        if (!need[b]) continue;
+        t->tw_tile[b] = cur; cur += (size_t)1 << b;
+        fill(t->tw_tile[b], 1u << (log_n - b), 1u << b);
+    }
+    Fr* w8dev = cur;  // 4 entries: omega^(j * n/8), j = 0..3 (n >= 8), else unused
+    if (log_n >= 3) {
+        fill(w8dev, 1u << (log_n - 3), 4);
+        Fr h[4];
+        ZK_CUDA(cudaMemcpyAsync(h, w8dev, sizeof h, cudaMemcpyDeviceToHost, s));
+        ZK_CUDA(cudaStreamSynchronize(s));
+        t->w8[0] = h[1]; t->w8[1] = h[2]; t->w8[2] = h[3];
+    } else {
+        // n = 2 or 4: only the size-4 root omega^(n/4) can be needed (as w8[1])
+        t->w8[0] = Fr::one();
+        t->w8[1] = (log_n == 2) ? omega : Fr::one();
+        t->w8[2] = Fr::one();
+    }
+    c.ntt_tables.push_back(t);
+    return t;
+}
+
+void ntt_release_tables(Context& c) {
+    for (NttTables* t : c.ntt_tables) {
+        cudaFree(t->block);
+        delete t;
+    }
+    c.ntt_tables.clear();
+}
+
+struct NttMods {
+    uint32_t in_mode = NTT_IN_PLAIN;
+    uint32_t n_in = 0;  // 0 = all rows valid
+    Fr in_tab[3];
+    const Fr* in_table = nullptr;
+    uint32_t in_table_mask = 0;
+    uint32_t out_mode = NTT_OUT_PLAIN;
+    Fr out_tab[3];
+    uint64_t n_keep = 0;  // 0 = keep all
+};
+
+template <int B, bool FIRST> static void launch_pass(const NttPassArgs& a, unsigned blocks, unsigned batch, cudaStream_t s) {
+    static bool configured = false;
+    constexpr int smem = 2 * NTT_TILE * sizeof(uint4);
+    if (!configured) {
+        ZK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<B, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    ntt_pass_kernel<B, FIRST><<<dim3(blocks, batch), NTT_THREADS, smem, s>>>(a);
+    ZK_LAUNCH_CHECK();
+}
+
+template <bool FIRST> static void launch_pass_b(int b, const NttPassArgs& a, unsigned blocks, unsigned batch, cudaStream_t s) {
+    switch (b) {
+        case 1: launch_pass<1, FIRST>(a, blocks, batch, s); break;
+        case 2: launch_pass<2, FIRST>(a, blocks, batch, s); break;
+        case 3: launch_pass<3, FIRST>(a, blocks, batch, s); break;
+        case 4: launch_pass<4, FIRST>(a, blocks, batch, s); break;
+        case 5: launch_pass<5, FIRST>(a, blocks, batch, s); break;
+        case 6: launch_pass<6, FIRST>(a, blocks, batch, s); break;
+        case 7: launch_pass<7, FIRST>(a, blocks, batch, s); break;
+        case 8: launch_pass<8, FIRST>(a, blocks, batch, s); break;
+        case 9: launch_pass<9, FIRST>(a, blocks, batch, s); break;
+        default: throw Error{"b200zk: bad pass width"};
+    }
+}
+
+// Transform `count` columns of 2^log_n elements.  `in` may equal `out` (in place);
+// `tmp` must hold count * 2^log_n elements when more than one pass is needed.
+static void ntt_run(Context& c, const Fr* in, uint64_t in_stride, Fr* out, uint64_t out_stride, Fr* tmp,
+                    size_t count, uint32_t log_n, const Fr& omega, const NttMods& mods, cudaStream_t s) {
+    if (count == 0) return;
+    NttTables* t = get_tables(c, omega, log_n, s);
+    const uint64_t n = (uint64_t)1 << log_n;
+    const int P = t->npass;
+    // destination of pass p (0-based); see DESIGN.md "NTT buffer rotation"
+    auto dst_of = [&](int p) -> Fr* {
+        if (P == 1) return out;
+        if (P % 2 == 0) return (p % 2 == 0) ? tmp : out;
+        if (p == P - 1) return out;      // odd P >= 3: last pass runs in place on `out`
+        return (p % 2 == 0) ? tmp : out;
+    };
+    const Fr* src = in;
+    uint64_t src_stride = in_stride;
+    uint32_t log_I = 0;
+    for (int p = 0; p < P; ++p) {
+        const int b = t->bits[p];
+        Fr* dst = dst_of(p);
+        const uint64_t dst_stride = (dst == tmp) ? n : out_stride;
+        NttPassArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = src;
+        a.out = dst;
+        a.log_n = log_n;
+        a.log_I = log_I;
+        a.log_cols = log_n - b;
+        a.last = (p == P - 1) ? 1u : 0u;
+        a.tw_tile = t->tw_tile[b];
+        a.tw_lo = t->tw_lo;
+        a.tw_hi = t->tw_hi;
+        a.tw_h = t->tw_h;
+        a.w8[0] = t->w8[0]; a.w8[1] = t->w8[1]; a.w8[2] = t->w8[2];
+        a.in_mode = (p == 0) ? mods.in_mode : (uint32_t)NTT_IN_PLAIN;
+        a.n_in = (p == 0 && mods.n_in) ? mods.n_in : (uint32_t)n;
+        for (int i = 0; i < 3; ++i) { a.in_tab[i] = mods.in_tab[i]; a.out_tab[i] = mods.out_tab[i]; }
+        a.in_table = mods.in_table;
+        a.in_table_mask = mods.in_table_mask;
+        a.out_mode = (p == P - 1) ? mods.out_mode : (uint32_t)NTT_OUT_PLAIN;
+        a.n_keep = (uint32_t)((p == P - 1 && mods.n_keep) ? mods.n_keep : n);
+        a.in_batch_stride = src_stride;
+        a.out_batch_stride = dst_stride;
+        const uint32_t ncols = 1u << a.log_cols;
+        const uint32_t C = 1u << (NTT_TILE_LOG - b);
+        const unsigned blocks = (ncols + C - 1) / C;
+        if (p == 0) launch_pass_b<true>(b, a, blocks, (unsigned)count, s);
+        else launch_pass_b<false>(b, a, blocks, (unsigned)count, s);
+        src = dst;
+        src_stride = dst_stride;
+        log_I += b;
+    }
+}
+
+static __global__ void fr_scale_table_kernel(Fr* a, size_t n, const Fr* table, uint32_t mask) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = ldg_fr(a + i) * ldg_fr(table + (i & mask));
+    st_fr(a + i, x);
+}
+
+static void check_batch(size_t stride, size_t count, uint64_t n) {
+    ZK_REQUIRE(count <= 65535, "batch count exceeds 65535");
+    ZK_REQUIRE(count <= 1 || stride >= n, "batch stride smaller than the transform");
+}
+
+// Host-buffer batch: gather columns into one device buffer, transform, scatter back.
+static void host_ntt(uint64_t* a, size_t stride, size_t count, uint32_t log_n, const Fr& omega, const NttMods& mods) {
+    ensure_init();
+    Context& c = ctx();
+    const uint64_t n = (uint64_t)1 << log_n;
+    check_batch(stride, count, n);
+    if (count == 0) return;
+    cudaStream_t s = c.stream;
+    Fr* io = (Fr*)c.ntt_io.get(count * n * sizeof(Fr));
+    Fr* tmp = (Fr*)c.ntt_tmp.get(count * n * sizeof(Fr));
+    ZK_CUDA(cudaMemcpy2DAsync(io, n * sizeof(Fr), a, stride * sizeof(Fr), n * sizeof(Fr), count,
+                              cudaMemcpyHostToDevice, s));
+    ntt_run(c, io, n, io, n, tmp, count, log_n, omega, mods, s);
+    ZK_CUDA(cudaMemcpy2DAsync(a, stride * sizeof(Fr), io, n * sizeof(Fr), n * sizeof(Fr), count,
+                              cudaMemcpyDeviceToHost, s));
+    ZK_CUDA(cudaStreamSynchronize(s));
+}
+
+static NttMods scale_mods(const uint64_t* divisor) {
+    NttMods m;
+    if (divisor) {
+        Fr d = fr_from_limbs(divisor);
+        m.out_mode = NTT_OUT_MOD3;
+        m.out_tab[0] = d; m.out_tab[1] = d; m.out_tab[2] = d;
+    }
+    return m;
+}
+
+static NttMods coset_in_mods(uint32_t k, const uint64_t* zeta) {
+    NttMods m;
+    Fr z = fr_from_limbs(zeta);
+    m.in_mode = NTT_IN_MOD3;
+    m.n_in = 1u << k;
+    m.in_tab[0] = Fr::one(); m.in_tab[1] = z; m.in_tab[2] = z * z;  // zeta^(i mod 3)
+    return m;
+}
+
+static NttMods coset_out_mods(const uint64_t* divisor, const uint64_t* zeta, size_t keep) {
+    NttMods m;
+    Fr d = fr_from_limbs(divisor);
+    Fr z = fr_from_limbs(zeta);
+    m.out_mode = NTT_OUT_MOD3;
+    // zeta^-(i mod 3): zeta^-1 = zeta^2, zeta^-2 = zeta (zeta^3 = 1)
+    m.out_tab[0] = d; m.out_tab[1] = d * (z * z); m.out_tab[2] = d * z;
+    m.n_keep = keep;
+    return m;
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+extern "C" {
+
+int b200zk_ntt(uint64_t* a, uint32_t log_n, const uint64_t omega[4]) {
+    return b200zk_ntt_many(a, (size_t)1 << log_n, 1, log_n, omega);
+}
+
+int b200zk_ntt_many(uint64_t* a, size_t stride, size_t count, uint32_t log_n, const uint64_t omega[4]) {
+    return guarded([&] {
+        ZK_REQUIRE(a && omega, "null argument");
+        if (log_n == 0) return;  // 1-point transform is the identity
+        host_ntt(a, stride, count, log_n, fr_from_limbs(omega), NttMods());
+    });
+}
+
+int b200zk_intt(uint64_t* a, uint32_t log_n, const uint64_t omega_inv[4], const uint64_t divisor[4]) {
+    return b200zk_intt_many(a, (size_t)1 << log_n, 1, log_n, omega_inv, divisor);
+}
+
+int b200zk_intt_many(uint64_t* a, size_t stride, size_t count, uint32_t log_n, const uint64_t omega_inv[4],
+                     const uint64_t divisor[4]) {
+    return guarded([&] {
+        ZK_REQUIRE(a && omega_inv && divisor, "null argument");
+        ZK_REQUIRE(log_n >= 1, "log_n must be >= 1");
+        host_ntt(a, stride, count, log_n, fr_from_limbs(omega_inv), scale_mods(divisor));
+    });
+}
+
+int b200zk_coeff_to_extended(const uint64_t* in, uint32_t k, uint64_t* out, uint32_t ext_k,
+                             const uint64_t extended_omega[4], const uint64_t zeta[4]) {
+    return b200zk_coeff_to_extended_many(in, (size_t)1 << k, out, (size_t)1 << ext_k, 1, k, ext_k, extended_omega,
+                                         zeta);
+}
+
+int b200zk_coeff_to_extended_many(const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride,
+                                  size_t count, uint32_t k, uint32_t ext_k, const uint64_t extended_omega[4],
+                                  const uint64_t zeta[4]) {
+    return guarded([&] {
+        ZK_REQUIRE(in && out && extended_omega && zeta, "null argument");
+        ZK_REQUIRE(ext_k >= k && ext_k >= 1, "extended_k must be >= k and >= 1");
+        ensure_init();
+        Context& c = ctx();
+        const uint64_t n = (uint64_t)1 << k, N = (uint64_t)1 << ext_k;
+        check_batch(in_stride, count, n);
+        check_batch(out_stride, count, N);
+        if (count == 0) return;
+        cudaStream_t s = c.stream;
+        Fr* din = (Fr*)c.ntt_aux.get(count * n * sizeof(Fr));
+        Fr* io = (Fr*)c.ntt_io.get(count * N * sizeof(Fr));
+        Fr* tmp = (Fr*)c.ntt_tmp.get(count * N * sizeof(Fr));
+        ZK_CUDA(cudaMemcpy2DAsync(din, n * sizeof(Fr), in, in_stride * sizeof(Fr), n * sizeof(Fr), count,
+                                  cudaMemcpyHostToDevice, s));
+        ntt_run(c, din, n, io, N, tmp, count, ext_k, fr_from_limbs(extended_omega), coset_in_mods(k, zeta), s);
+        ZK_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(Fr), io, N * sizeof(Fr), N * sizeof(Fr), count,
+                                  cudaMemcpyDeviceToHost, s));
+        ZK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200zk_extended_to_coeff(const uint64_t* a, uint32_t ext_k, const uint64_t extended_omega_inv[4],
+                             const uint64_t extended_ifft_divisor[4], const uint64_t zeta[4], uint64_t* out,
+                             size_t keep) {
+    return guarded([&] {
+        ZK_REQUIRE(a && out && extended_omega_inv && extended_ifft_divisor && zeta, "null argument");
+        ZK_REQUIRE(ext_k >= 1, "extended_k must be >= 1");
+        const uint64_t N = (uint64_t)1 << ext_k;
+        ZK_REQUIRE(keep <= N, "keep exceeds the extended domain");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = c.stream;
+        Fr* din = (Fr*)c.ntt_aux.get(N * sizeof(Fr));
+        Fr* io = (Fr*)c.ntt_io.get(N * sizeof(Fr));
+        Fr* tmp = (Fr*)c.ntt_tmp.get(N * sizeof(Fr));
+        ZK_CUDA(cudaMemcpyAsync(din, a, N * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        NttMods m = coset_out_mods(extended_ifft_divisor, zeta, keep);
+        if (keep == 0) return;
+        ntt_run(c, din, N, io, N, tmp, 1, ext_k, fr_from_limbs(extended_omega_inv), m, s);
+        ZK_CUDA(cudaMemcpyAsync(out, io, keep * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+        ZK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200zk_divide_by_vanishing(uint64_t* h, uint32_t ext_k, const uint64_t* t_evaluations, uint32_t t_len) {
+    return guarded([&] {
+        ZK_REQUIRE(h && t_evaluations, "null argument");
+        ZK_REQUIRE(t_len != 0 && (t_len & (t_len - 1)) == 0, "t_len must be a power of two");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = c.stream;
+        const uint64_t N = (uint64_t)1 << ext_k;
+        Fr* io = (Fr*)c.ntt_io.get(N * sizeof(Fr));
+        Fr* tab = (Fr*)c.ntt_aux.get((size_t)t_len * sizeof(Fr));
+        ZK_CUDA(cudaMemcpyAsync(io, h, N * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        ZK_CUDA(cudaMemcpyAsync(tab, t_evaluations, (size_t)t_len * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        fr_scale_table_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(io, N, tab, t_len - 1);
+        ZK_LAUNCH_CHECK();
+        ZK_CUDA(cudaMemcpyAsync(h, io, N * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+        ZK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200zk_ntt_dev(void* d_a, size_t stride, size_t count, uint32_t log_n, const uint64_t omega[4],
+                   const uint64_t* divisor_or_null, void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_a && omega, "null argument");
+        if (log_n == 0) return;
+        ensure_init();
+        Context& c = ctx();
+        const uint64_t n = (uint64_t)1 << log_n;
+        check_batch(stride, count, n);
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        Fr* tmp = (Fr*)c.ntt_tmp.get(count * n * sizeof(Fr));
+        ntt_run(c, (Fr*)d_a, stride, (Fr*)d_a, stride, tmp, count, log_n, fr_from_limbs(omega),
+                scale_mods(divisor_or_null), s);
+    });
+}
+
+int b200zk_coeff_to_extended_dev(const void* d_in, size_t in_stride, void* d_out, size_t out_stride, size_t count,
+                                 uint32_t k, uint32_t ext_k, const uint64_t extended_omega[4],
+                                 const uint64_t zeta[4], void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_in && d_out && extended_omega && zeta, "null argument");
+        ZK_REQUIRE(ext_k >= k && ext_k >= 1, "extended_k must be >= k and >= 1");
+        ZK_REQUIRE(d_in != d_out, "coeff_to_extended cannot run in place");
+        ensure_init();
+        Context& c = ctx();
+        const uint64_t n = (uint64_t)1 << k, N = (uint64_t)1 << ext_k;
+        check_batch(in_stride, count, n);
+        check_batch(out_stride, count, N);
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        Fr* tmp = (Fr*)c.ntt_tmp.get(count * N * sizeof(Fr));
+        ntt_run(c, (const Fr*)d_in, in_stride, (Fr*)d_out, out_stride, tmp, count, ext_k,
+                fr_from_limbs(extended_omega), coset_in_mods(k, zeta), s);
+    });
+}
+
+int b200zk_extended_to_coeff_dev(const void* d_a, uint32_t ext_k, const uint64_t extended_omega_inv[4],
+                                 const uint64_t extended_ifft_divisor[4], const uint64_t zeta[4],
+                                 const void* d_t_evaluations_or_null, uint32_t t_len, void* d_out, size_t keep,
+                                 void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_a && d_out && extended_omega_inv && extended_ifft_divisor && zeta, "null argument");
+        const uint64_t N = (uint64_t)1 << ext_k;
+        ZK_REQUIRE(ext_k >= 1 && keep <= N, "bad extended_k / keep");
+        ZK_REQUIRE(d_a != d_out, "extended_to_coeff_dev cannot run in place");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        if (keep == 0) return;
+        NttMods m = coset_out_mods(extended_ifft_divisor, zeta, keep);
+        if (d_t_evaluations_or_null) {
+            ZK_REQUIRE(t_len != 0 && (t_len & (t_len - 1)) == 0, "t_len must be a power of two");
+            m.in_mode = NTT_IN_TABLE;
+            m.in_table = (const Fr*)d_t_evaluations_or_null;
+            m.in_table_mask = t_len - 1;
+        }
+        // result needs N slots while passes run; d_out may be shorter, so work in scratch
+        Fr* io = (Fr*)c.ntt_io.get(N * sizeof(Fr));
+        Fr* tmp = (Fr*)c.ntt_tmp.get(N * sizeof(Fr));
+        ntt_run(c, (const Fr*)d_a, N, io, N, tmp, 1, ext_k, fr_from_limbs(extended_omega_inv), m, s);
+        ZK_CUDA(cudaMemcpyAsync(d_out, io, keep * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+    });
+}
+
+}  // extern "C"
