@@ -1,0 +1,114 @@
+"""GPU parity of the MSM path through the C ABI against the oracle (same group element,
+compared in affine as SURVEY.md section 8 c prescribes)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as bn
+from oracle import c_oracle as co
+from util import GOLDEN, jac_affine
+
+pytestmark = pytest.mark.gpu
+
+
+def test_msm_golden(zk):
+    z = np.load(GOLDEN / "msm_kat.npz")
+    for name in z["names"].tolist():
+        got = jac_affine(zk.best_multiexp(z[f"s_{name}"], z[f"p_{name}"]))
+        exp = bn.g1_affine_array_to_points(z[f"r_{name}"][None, :])[0]
+        assert got == exp, name
+
+
+def test_msm_empty_is_identity(zk):
+    out = zk.best_multiexp(np.zeros((0, 4), dtype=np.uint64), np.zeros((0, 8), dtype=np.uint64))
+    assert jac_affine(out) is None
+    assert bn.array_to_ints(out)[1] == bn.FQ_MONT["R"]        # (0, 1, 0) like G1::identity()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 255, 1000, 4097, 1 << 14, (1 << 16) + 3, 1 << 18])
+def test_msm_vs_oracle(zk, n):
+    s = co.gen_scalars(0xA11CE000 + n, n)
+    p = co.gen_points(0xBA5E0000 + n, n)
+    assert jac_affine(zk.best_multiexp(s, p)) == jac_affine(co.best_multiexp(s, p))
+
+
+def test_msm_adversarial_scalar_sets(zk):
+    n = 6000
+    p = co.gen_points(9, n)
+    sets = {
+        "all r-1": bn.fr_array_from_canonical([bn.R - 1] * n),
+        "all one": bn.fr_array_from_canonical([1] * n),
+        "all zero": bn.fr_array_from_canonical([0] * n),
+        "small": bn.fr_array_from_canonical([(i * 7) % 65536 for i in range(n)]),
+        "window boundaries": bn.fr_array_from_canonical([(1 << (i % 254)) - (i % 3) for i in range(n)]),
+    }
+    sparse = co.gen_scalars(5, n)
+    sparse[np.arange(n) % 10 != 0] = 0
+    sets["90% zero"] = sparse
+    for name, s in sets.items():
+        assert jac_affine(zk.best_multiexp(s, p)) == jac_affine(co.best_multiexp(s, p)), name
+
+
+def test_msm_adversarial_points(zk):
+    n = 3000
+    s = co.gen_scalars(4, n)
+    same = np.repeat(co.gen_points(3, 1), n, axis=0)          # one bucket run per window, P + P cases
+    assert jac_affine(zk.best_multiexp(s, same)) == jac_affine(co.best_multiexp(s, same))
+    p = co.gen_points(3, n)
+    p[::3] = 0                                                # identity bases
+    assert jac_affine(zk.best_multiexp(s, p)) == jac_affine(co.best_multiexp(s, p))
+    pts = bn.g1_affine_array_to_points(p[1:3])
+    p[5] = bn.g1_affine_array_from_points([bn.g1_neg(pts[0])])[0]   # P and -P with equal scalars
+    s[5] = s[1]
+    assert jac_affine(zk.best_multiexp(s, p)) == jac_affine(co.best_multiexp(s, p))
+
+
+def test_params_kzg_commit(zk):
+    n = 1 << 12
+    g, gl = co.gen_points(21, n), co.gen_points(22, n)
+    params = zk.ParamsKZG(g, gl)
+    poly = co.gen_scalars(23, n)
+    assert jac_affine(params.commit(poly)) == jac_affine(co.best_multiexp(poly, g))
+    assert jac_affine(params.commit_lagrange(poly)) == jac_affine(co.best_multiexp(poly, gl))
+    short = poly[:1000]                                       # poly shorter than the SRS
+    assert jac_affine(params.commit(short)) == jac_affine(co.best_multiexp(short, g[:1000]))
+    with pytest.raises(AssertionError):
+        params.commit(co.gen_scalars(1, n + 1))
+    params.close()
+
+
+def test_g1_sum_matches_fold(zk):
+    n = 900
+    s, p = co.gen_scalars(31, n), co.gen_points(32, n)
+    parts = np.stack([zk.best_multiexp(s[i:i + 300], p[i:i + 300]) for i in range(0, n, 300)])
+    ident = zk.best_multiexp(s[:0], p[:0])
+    parts = np.concatenate([parts, ident[None, :]])
+    assert jac_affine(zk.g1_sum(parts)) == jac_affine(co.best_multiexp(s, p))
+
+
+@pytest.mark.parametrize("k", [20, 22])
+def test_msm_full_size_linearity(zk, k):
+    """BASELINE sizes: MSM(s, P) with P_i = [t_i]G equals [sum s_i t_i] G (checked with
+    Python integers), and MSM(2s, P) == 2 MSM(s, P)."""
+    import torch
+
+    lib = zk.load()
+    n = 1 << k
+    ds = torch.empty(n * 4, dtype=torch.int64, device="cuda")
+    db = torch.empty(n * 8, dtype=torch.int64, device="cuda")
+    zk.check(lib.b200zk_gen_scalars_dev(C.c_void_p(ds.data_ptr()), n, 0xA11CE000 + k, 0))
+    zk.check(lib.b200zk_gen_points_dev(C.c_void_p(db.data_ptr()), n, 0xBA5E0000 + k, 0))
+    out = np.zeros(12, dtype=np.uint64)
+    zk.check(lib.b200zk_msm_g1_dev(C.c_void_p(ds.data_ptr()), C.c_void_p(db.data_ptr()), n, C.c_void_p(out.ctypes.data), None))
+    s = ds.cpu().numpy().view(np.uint64).reshape(n, 4)
+    # t_i stream of oracle/bn254.py seeded_point_scalar, vectorised
+    with np.errstate(over="ignore"):
+        t = bn._splitmix64_np(np.uint64(((0xBA5E0000 + k) << 32) & ((1 << 64) - 1)) + np.arange(n, dtype=np.uint64)) | np.uint64(1)
+    rinv = pow(1 << 256, -1, bn.R)
+    acc = 0
+    svals = bn.array_to_ints(s)
+    for si, ti in zip(svals, t.tolist()):
+        acc += si * ti
+    scalar = acc % bn.R * rinv % bn.R                          # scalars are Montgomery representatives
+    assert jac_affine(out) == bn.g1_mul(bn.G1_GEN, scalar)
