@@ -91,7 +91,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     std::mutex mu;  // the ABI is thread-safe but not concurrent (SURVEY.md section 8 b)
     Arena ntt_io, ntt_tmp, ntt_aux;
-    Arena msm_scalars, msm_bases, msm_work;
+    Arena msm_scalars, msm_bases, msm_work, msm_carry;
     Arena misc;
     PinnedArena pinned;
     std::vector<NttTables*> ntt_tables;

@@ -155,7 +155,7 @@ int b200zk_shutdown(void) {
         cudaStreamSynchronize(c.stream);
         ntt_release_tables(c);
         msm_release_bases(c);
-        for (Arena* a : {&c.ntt_io, &c.ntt_tmp, &c.ntt_aux, &c.msm_scalars, &c.msm_bases, &c.msm_work, &c.misc})
+        for (Arena* a : {&c.ntt_io, &c.ntt_tmp, &c.ntt_aux, &c.msm_scalars, &c.msm_bases, &c.msm_work, &c.msm_carry, &c.misc})
             a->release();
         c.pinned.release();
         cudaStreamDestroy(c.stream);

@@ -367,11 +367,42 @@ __global__ void g1_sum_kernel(const G1Jacobian* __restrict__ pts, uint32_t count
 }
 
 // ------------------------------------------------------------------ host pipeline
+// ------------------------------------------------------------- per-stage timing
+// Optional CUDA-event bracketing of the pipeline stages (b200zk_msm_profile), used by
+// bench.py to time the dominant kernel on the stream it runs on.
+enum MsmStage { MSM_ST_HIST = 0, MSM_ST_SCAN, MSM_ST_SCATTER, MSM_ST_SYNC, MSM_ST_ACCUM, MSM_ST_COMBINE,
+                MSM_ST_REDUCE, MSM_ST_REDUCE_COMBINE, MSM_ST_FOLD, MSM_ST_END, MSM_ST_COUNT };
+struct MsmInfo { uint64_t n; uint32_t c, nwin, npairs, chunk; };
+static MsmInfo g_msm_info = {0, 0, 0, 0, 0};
+static bool g_msm_profile = false;
+static cudaEvent_t g_msm_ev[MSM_ST_COUNT];
+static bool g_msm_ev_made = false, g_msm_ev_valid[MSM_ST_COUNT];
+static cudaStream_t g_msm_ev_stream = nullptr;
+
+struct StageTimer {
+    cudaStream_t s;
+    bool on;
+    StageTimer(Context&, cudaStream_t st) : s(st), on(g_msm_profile) {
+        if (!on) return;
+        if (!g_msm_ev_made) {
+            for (int i = 0; i < MSM_ST_COUNT; ++i) ZK_CUDA(cudaEventCreate(&g_msm_ev[i]));
+            g_msm_ev_made = true;
+        }
+        for (int i = 0; i < MSM_ST_COUNT; ++i) g_msm_ev_valid[i] = false;
+        g_msm_ev_stream = st;
+    }
+    void mark(int stage) {
+        if (!on) return;
+        ZK_CUDA(cudaEventRecord(g_msm_ev[stage], s));
+        g_msm_ev_valid[stage] = true;
+    }
+};
+
 static uint32_t choose_window(size_t n) {
     // minimise 10*n*W (mixed adds) + 30*W*2^(c-1) (two full adds per bucket + slack)
     double best = 1e300;
     uint32_t bc = 4;
-    for (uint32_t c = 4; c <= 20; ++c) {
+    for (uint32_t c = 4; c <= 23; ++c) {
         const double W = (255 + c - 1) / c;
         const double cost = 10.0 * (double)n * W + 30.0 * W * (double)(1u << (c - 1));
         if (cost < best) { best = cost; bc = c; }
@@ -423,14 +454,11 @@ static void msm_device(Context& c, const Fr* d_scalars, const G1Affine* d_bases,
     const size_t max_pairs = n * P.nwin;
     ZK_REQUIRE(max_pairs < ((size_t)1 << 32), "MSM too large for 32-bit pair offsets");
 
-    // ---- carve the work arena
+    // ---- carve the sort arena (sizes known up front)
     const uint32_t scan_blocks = (uint32_t)((P.nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    const uint32_t Lmin = 4;
-    const size_t max_threads0 = (max_pairs + Lmin - 1) / Lmin;
     const uint32_t seglen = 32;
     const uint32_t segs_per_win = (P.nb + seglen - 1) / seglen;
     const size_t red_entries = (size_t)segs_per_win * P.nwin;
-    const size_t carry_cap = std::max(max_threads0, red_entries);
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_hist = carve(((size_t)P.nkeys + 1) * 4);
@@ -440,10 +468,6 @@ static void msm_device(Context& c, const Fr* d_scalars, const G1Affine* d_bases,
     const size_t o_total = carve(256);
     const size_t o_sorted = carve(max_pairs * 4);
     const size_t o_buckets = carve((size_t)P.nkeys * sizeof(G1Xyzz));
-    const size_t o_keyA = carve(carry_cap * 4);
-    const size_t o_ptA = carve(carry_cap * sizeof(G1Xyzz));
-    const size_t o_keyB = carve((carry_cap / 8 + 64) * 4);
-    const size_t o_ptB = carve((carry_cap / 8 + 64) * sizeof(G1Xyzz));
     const size_t o_win = carve((size_t)P.nwin * sizeof(G1Xyzz));
     char* base = (char*)c.msm_work.get(off);
     uint32_t* hist = (uint32_t*)(base + o_hist);
@@ -453,53 +477,74 @@ static void msm_device(Context& c, const Fr* d_scalars, const G1Affine* d_bases,
     uint32_t* total = (uint32_t*)(base + o_total);
     uint32_t* sorted = (uint32_t*)(base + o_sorted);
     G1Xyzz* buckets = (G1Xyzz*)(base + o_buckets);
-    uint32_t* keyA = (uint32_t*)(base + o_keyA);
-    G1Xyzz* ptA = (G1Xyzz*)(base + o_ptA);
-    uint32_t* keyB = (uint32_t*)(base + o_keyB);
-    G1Xyzz* ptB = (G1Xyzz*)(base + o_ptB);
     G1Xyzz* win = (G1Xyzz*)(base + o_win);
 
+    StageTimer T(c, s);
     // ---- 1-3: sort (bucket, point) pairs
     ZK_CUDA(cudaMemsetAsync(hist, 0, ((size_t)P.nkeys + 1) * 4, s));
     ZK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)P.nkeys * sizeof(G1Xyzz), s));
     ZK_CUDA(cudaMemsetAsync(win, 0, (size_t)P.nwin * sizeof(G1Xyzz), s));
     const unsigned sblocks = (unsigned)((n + 255) / 256);
+    T.mark(MSM_ST_HIST);
     msm_hist_kernel<<<sblocks, 256, 0, s>>>(d_scalars, n, P.c, P.nwin, hist);
     ZK_LAUNCH_CHECK();
+    T.mark(MSM_ST_SCAN);
     scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(hist, start, bsum, P.nkeys);
     ZK_LAUNCH_CHECK();
     scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(bsum, scan_blocks, total);
     ZK_LAUNCH_CHECK();
     scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, P.nkeys, total);
     ZK_LAUNCH_CHECK();
+    T.mark(MSM_ST_SCATTER);
     msm_scatter_kernel<<<sblocks, 256, 0, s>>>(d_scalars, n, P.c, P.nwin, cursor, sorted);
     ZK_LAUNCH_CHECK();
+    T.mark(MSM_ST_SYNC);
     uint32_t npairs = 0;
     ZK_CUDA(cudaMemcpyAsync(&npairs, total, 4, cudaMemcpyDeviceToHost, s));
     ZK_CUDA(cudaStreamSynchronize(s));
 
+    // chunk length: keep >= ~1024 threads per SM in flight, between 4 and 32 pairs each
+    const uint32_t L = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(4, npairs / ((uint64_t)c.sm_count * 1024)));
+    const uint32_t nthreads0 = (npairs + L - 1) / L;
+    // ---- carve the carry arena now that the pair count is known
+    const size_t carry_cap = std::max<size_t>(std::max<size_t>(nthreads0, red_entries), 64);
+    off = 0;
+    const size_t o_keyA = carve(carry_cap * 4);
+    const size_t o_ptA = carve(carry_cap * sizeof(G1Xyzz));
+    const size_t o_keyB = carve((carry_cap / 16 + 64) * 4);
+    const size_t o_ptB = carve((carry_cap / 16 + 64) * sizeof(G1Xyzz));
+    char* cbase = (char*)c.msm_carry.get(off);
+    uint32_t* keyA = (uint32_t*)(cbase + o_keyA);
+    G1Xyzz* ptA = (G1Xyzz*)(cbase + o_ptA);
+    uint32_t* keyB = (uint32_t*)(cbase + o_keyB);
+    G1Xyzz* ptB = (G1Xyzz*)(cbase + o_ptB);
+    g_msm_info.n = n; g_msm_info.c = P.c; g_msm_info.nwin = P.nwin; g_msm_info.npairs = npairs; g_msm_info.chunk = L;
+
     // ---- 4: accumulate
+    T.mark(MSM_ST_ACCUM);
     if (npairs > 0) {
-        // chunk length: keep >= ~1024 threads per SM in flight, between 4 and 32 pairs each
-        uint32_t L = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(Lmin, npairs / ((uint64_t)c.sm_count * 1024)));
-        const uint32_t nthreads = (npairs + L - 1) / L;
-        msm_accum_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(d_bases, sorted, start, P.nkeys, npairs, L, buckets,
-                                                                keyA, ptA, nthreads);
+        msm_accum_kernel<<<(nthreads0 + 127) / 128, 128, 0, s>>>(d_bases, sorted, start, P.nkeys, npairs, L, buckets,
+                                                                 keyA, ptA, nthreads0);
         ZK_LAUNCH_CHECK();
-        run_combine_levels(keyA, ptA, keyB, ptB, nthreads, buckets, s);
+        T.mark(MSM_ST_COMBINE);
+        run_combine_levels(keyA, ptA, keyB, ptB, nthreads0, buckets, s);
     }
 
     // ---- 5: per-window running sums, then keyed reduction with key = window
+    T.mark(MSM_ST_REDUCE);
     {
         const uint32_t nthreads = (uint32_t)red_entries;
         msm_reduce_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(buckets, P.nb, seglen, segs_per_win, P.nwin, keyA,
                                                                  ptA);
         ZK_LAUNCH_CHECK();
+        T.mark(MSM_ST_REDUCE_COMBINE);
         run_combine_levels(keyA, ptA, keyB, ptB, nthreads, win, s);
     }
+    T.mark(MSM_ST_FOLD);
     // ---- 6: fold the windows
     msm_fold_kernel<<<1, 32, 0, s>>>(win, P.nwin, P.c, d_out);
     ZK_LAUNCH_CHECK();
+    T.mark(MSM_ST_END);
 }
 
 static void copy_point_out(Context& c, const G1Jacobian* d, uint64_t* out, cudaStream_t s) {
@@ -600,6 +645,27 @@ int b200zk_msm_g1_dev_async(const void* d_scalars, const void* d_bases, size_t n
         Context& c = ctx();
         cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
         msm_device(c, (const Fr*)d_scalars, (const G1Affine*)d_bases, n, (G1Jacobian*)d_out_xyz, s);
+    });
+}
+
+int b200zk_msm_profile(int enable) {
+    return guarded([&] { g_msm_profile = enable != 0; });
+}
+
+int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]) {
+    return guarded([&] {
+        ZK_REQUIRE(ms_out && capacity >= MSM_ST_COUNT - 1 && info_out, "bad arguments");
+        ZK_REQUIRE(g_msm_ev_made, "no profiled MSM has run");
+        ZK_CUDA(cudaStreamSynchronize(g_msm_ev_stream));
+        for (int i = 0; i + 1 < MSM_ST_COUNT; ++i) {
+            ms_out[i] = 0.f;
+            if (!g_msm_ev_valid[i]) continue;
+            int j = i + 1;
+            while (j < MSM_ST_COUNT && !g_msm_ev_valid[j]) ++j;
+            if (j < MSM_ST_COUNT) ZK_CUDA(cudaEventElapsedTime(&ms_out[i], g_msm_ev[i], g_msm_ev[j]));
+        }
+        info_out[0] = g_msm_info.n; info_out[1] = g_msm_info.c; info_out[2] = g_msm_info.nwin;
+        info_out[3] = g_msm_info.npairs; info_out[4] = g_msm_info.chunk;
     });
 }
 

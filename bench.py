@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""bench.py — the BN254 MSM + Fr NTT hot path of the Halo2/KZG prover on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--k 24] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): "standalone BN254 MSM and Fr NTT sweep k=16..26 on
+synthetic scalars/points".  One *step* = one `best_multiexp` over 2^k seeded (scalar,
+point) pairs plus one `best_fft` over 2^k seeded scalars, per GPU.  With N GPUs the MSM
+is the north-star point-range split: rank r owns points [r*2^k, (r+1)*2^k) of one
+N*2^k-point MSM, partial sums are combined by a one-point-per-rank gather (NCCL
+all_gather of 96 B) + a fold on rank 0; the NTT columns are independent per rank.
+Per-GPU work is fixed, so scaling is "weak".
+
+Printed line: see the contract in the task statement; `value` is Mpts/s through the
+whole step with inputs resident in HBM; `e2e` is the same through the host-buffer C-ABI
+calls (`b200zk_msm_g1`, `b200zk_ntt`) with pinned host buffers, H2D/D2H inside the timed
+region; `roofline` is the dominant kernel (bucket accumulation) against the measured
+integer-pipe modmul peak, `roofline_ntt` the NTT against the measured HBM copy peak.
+`--impl reference` times the restated CPU baseline (oracle/halo2_oracle.c; the
+reference's Rust prover cannot be built here: no cargo, dependencies not vendored).
+`--sweep` prints the k = 16..26 table used in DESIGN.md (not a driver line).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "anon-aadhaar-halo2_b200"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "MSM Mpts/s (step = BN254 G1 best_multiexp 2^k + Fr best_fft 2^k)"
+UNIT = "Mpts/s"
+SEED_S, SEED_P = 0xA11CE000, 0xBA5E0000
+
+
+def fr_limbs(x: int) -> np.ndarray:
+    from b200zk.api import fr_limbs as f
+    return f(x)
+
+
+def omega_for(k: int) -> int:
+    from b200zk.api import FR_MODULUS, FR_ROOT_OF_UNITY, FR_S
+    w = FR_ROOT_OF_UNITY
+    for _ in range(k, FR_S):
+        w = w * w % FR_MODULUS
+    return w
+
+
+def msm_modmul_model(npairs: int) -> float:
+    """Algorithmic work of the bucket-accumulation kernel: one XYZZ mixed addition
+    (8M + 2S = 10 field multiplications) per (point, window) pair."""
+    return 10.0 * npairs
+
+
+def ntt_alg_bytes(k: int) -> float:
+    """SURVEY.md section 8 d: 64 * n * ceil(k / 12)."""
+    return 64.0 * (1 << k) * max(1, -(-k // 12))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_step(co, k: int, threads: int, scalars=None, points=None):
+    """One step of the restated CPU baseline at size 2^k; returns (seconds, msm_s, fft_s)."""
+    n = 1 << k
+    if scalars is None:
+        scalars = co.gen_scalars(SEED_S + k, n)
+        points = co.gen_points(SEED_P + k, n, threads=threads)
+    w = fr_limbs(omega_for(k))
+    t0 = time.perf_counter()
+    co.best_multiexp(scalars, points, threads)
+    t1 = time.perf_counter()
+    co.best_fft(scalars, w, k, threads)
+    t2 = time.perf_counter()
+    return t2 - t0, t1 - t0, t2 - t1
+
+
+def run_reference(args) -> None:
+    """--impl reference: the restated CPU baseline on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import c_oracle as co
+    co.build()
+    threads = co.host_threads()
+    k = args.cpu_k
+    n = 1 << k
+    scalars = co.gen_scalars(SEED_S + k, n)
+    points = co.gen_points(SEED_P + k, n, threads=threads)
+    for _ in range(args.warmup):
+        cpu_step(co, k, threads, scalars, points)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(co, k, threads, scalars, points)
+    dt = time.perf_counter() - t0
+    value = args.steps * n / dt / 1e6
+    sample = f"each step = best_multiexp + best_fft at 2^{k} (bounded sample of the 2^{args.k} workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (Montgomery, 254-bit)",
+        "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated CPU baseline (C port of halo2_proofs best_multiexp/best_fft); the reference's Rust "
+                "prover cannot be built in this image (no cargo, git dependencies not vendored)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world: int) -> dict:
+    return {
+        "workload": f"BASELINE.json configs[1]: standalone BN254 MSM + Fr NTT at k={args.k} "
+                    f"(2^{args.k} points and scalars per GPU, seeds 0xA11CE000+k / 0xBA5E0000+k)",
+        "k": args.k, "points_per_gpu": 1 << args.k, "global_points": world << args.k,
+        "parallelism": f"point-range split x{world}, one-point-per-rank gather" if world > 1 else "single GPU",
+        "l2": "inputs (96 B/point + 32 B/NTT element, >= 2 GiB at k=24) exceed the 126 MB L2; no flush needed",
+    }
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--k", type=int, default=24, help="log2 points per GPU")
+    ap.add_argument("--cpu-k", type=int, default=20, help="log2 size of the bounded CPU sample")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="print the k=16..26 table instead of the driver line")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import b200zk
+    from b200zk.api import _ptr
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200zk product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    b200zk.init(local_rank)
+    lib = b200zk.load()
+    dev = torch.device("cuda", local_rank)
+
+    if args.sweep:
+        sweep(args, torch, b200zk, lib, dev)
+        return
+
+    k, n = args.k, 1 << args.k
+    stream = torch.cuda.Stream(device=dev)
+    st = C.c_void_p(stream.cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+
+    # ---- synthetic inputs, generated in HBM (rank r owns the r-th slice of the global MSM)
+    d_scal = torch.empty(n * 4, dtype=torch.int64, device=dev)
+    d_base = torch.empty(n * 8, dtype=torch.int64, device=dev)
+    d_ntt = torch.empty(n * 4, dtype=torch.int64, device=dev)
+    b200zk.check(lib.b200zk_gen_scalars_dev(vp(d_scal), n, SEED_S + k, rank * n))
+    b200zk.check(lib.b200zk_gen_points_dev(vp(d_base), n, SEED_P + k, rank * n))
+    d_ntt.copy_(d_scal)
+    d_pt = torch.zeros(12, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(world * 12, dtype=torch.int64, device=dev)
+    omega = fr_limbs(omega_for(k))
+    peak_modmul = b200zk.modmul_peak(4096)
+    result_holder = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ntt_ev = []
+
+    def step(timed: bool):
+        with torch.cuda.stream(stream):
+            b200zk.check(lib.b200zk_msm_g1_dev_async(vp(d_scal), vp(d_base), n, vp(d_pt), st))
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, d_pt)
+                if rank == 0:
+                    pts = gathered.cpu().numpy().view(np.uint64).reshape(world, 12)
+                    result_holder["point"] = b200zk.g1_sum(np.ascontiguousarray(pts))
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            b200zk.check(lib.b200zk_ntt_dev(vp(d_ntt), n, 1, k, _ptr(omega), None, st))
+            e1.record(stream)
+            if timed:
+                ntt_ev.append((e0, e1))
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    b200zk.check(lib.b200zk_msm_profile(1))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = b200zk.kernel_launches()
+    stage_ms = []
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+        ms = (C.c_float * 9)()
+        info = (C.c_uint64 * 5)()
+        b200zk.check(lib.b200zk_msm_last_stages(ms, 9, info))
+        stage_ms.append(list(ms))
+    ev1.record(stream)
+    barrier()
+    launches = b200zk.kernel_launches() - launches0
+    total_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    b200zk.check(lib.b200zk_msm_profile(0))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (bucket accumulation) + the NTT
+    info = list(info)
+    npairs = int(info[3])
+    names = ["hist", "scan", "scatter", "sync", "accumulate", "combine", "reduce", "reduce_combine", "fold"]
+    mean_stage = {nm: statistics.mean(s[i] for s in stage_ms) for i, nm in enumerate(names)}
+    acc_ms = mean_stage["accumulate"]
+    achieved_modmul = msm_modmul_model(npairs) / (acc_ms * 1e-3)
+    ntt_ms = statistics.mean(a.elapsed_time(b) for a, b in ntt_ev)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    traffic = {}
+    try:
+        traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+    except Exception:
+        pass
+    ntt_gbs = ntt_alg_bytes(k) / (ntt_ms * 1e-3) / 1e9
+    ntt_modmul = (1 << k) * (k / 2 + 2 * (max(1, -(-k // 9)) - 1)) / (ntt_ms * 1e-3)
+    roofline = {
+        "kernel": "msm_accum_kernel", "bound": "int",
+        "achieved": achieved_modmul / 1e9, "peak": peak_modmul / 1e9, "unit": "Gmodmul/s",
+        "frac": achieved_modmul / peak_modmul,
+        "peak_source": "b200zk_modmul_peak: register-resident Fq Montgomery chains on all SMs, measured in this run",
+        "algorithmic_work": "10 modmul per (point, window) pair x pairs per launch",
+        "pairs_per_launch": npairs, "kernel_ms": acc_ms,
+        "traffic": traffic.get(f"msm_accum_kernel@k{k}"),
+        "note": "modular integer arithmetic on the IMAD pipe (BASELINE.json north_star): HBM traffic is "
+                "64 B/pair, far from the bound",
+    }
+    roofline_ntt = {
+        "kernel": "ntt_pass_kernel (all passes of one transform)", "bound": "hbm",
+        "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak,
+        "peak_source": hbm_src, "algorithmic_bytes": ntt_alg_bytes(k), "kernel_ms": ntt_ms,
+        "int_frac": ntt_modmul / peak_modmul,
+        "traffic": traffic.get(f"ntt@k{k}"),
+        "note": "254-bit butterflies make the transform integer-bound on B200: int_frac is the fraction of the "
+                "measured modmul peak (k/2 butterfly + 2 twiddle multiplications per element per pass boundary)",
+    }
+
+    # ---- e2e: the host-buffer C-ABI calls, pinned host memory, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_scal = torch.empty(n * 4, dtype=torch.int64, pin_memory=True)
+        h_base = torch.empty(n * 8, dtype=torch.int64, pin_memory=True)
+        h_ntt = torch.empty(n * 4, dtype=torch.int64, pin_memory=True)
+        h_scal.copy_(d_scal); h_base.copy_(d_base); h_ntt.copy_(d_scal)
+        torch.cuda.synchronize()
+        out = np.zeros(12, dtype=np.uint64)
+
+        def e2e_step():
+            b200zk.check(lib.b200zk_msm_g1(vp(h_scal), vp(h_base), n, _ptr(out)))
+            if world > 1:
+                d_pt.copy_(torch.from_numpy(out.view(np.int64)))
+                dist.all_gather_into_tensor(gathered, d_pt)
+                if rank == 0:
+                    pts = gathered.cpu().numpy().view(np.uint64).reshape(world, 12)
+                    b200zk.g1_sum(np.ascontiguousarray(pts))
+            b200zk.check(lib.b200zk_ntt(vp(h_ntt), k, _ptr(omega)))
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * n * args.steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": world * n * (32 + 64 + 32), "d2h_bytes_per_step": world * (n * 32 + 96),
+               "ms_per_step": 1e3 * dt / args.steps,
+               "api": "b200zk_msm_g1 + b200zk_ntt on pinned host buffers (bases re-uploaded every call, as "
+                      "best_multiexp receives them)"}
+        del h_scal, h_base, h_ntt
+
+    # ---- restated CPU baseline on this box's host cores (rank 0, N = 1)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import c_oracle as co
+        co.build()
+        threads = co.host_threads()
+        ck = args.cpu_k
+        secs, msm_s, fft_s = cpu_step(co, ck, threads)
+        cpu_baseline = {"value": (1 << ck) / secs / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"one step at 2^{ck} (best_multiexp {msm_s:.2f} s + best_fft {fft_s:.2f} s); "
+                                  f"C restatement of the rayon CPU path, {threads} threads",
+                        "msm_mpts_per_s": (1 << ck) / msm_s / 1e6, "ntt_melem_per_s": (1 << ck) / fft_s / 1e6}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 limbs (254-bit Montgomery Fr/Fq)", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_ntt": roofline_ntt, "cpu_baseline": cpu_baseline,
+            "msm": {"ms": sum(mean_stage.values()), "mpts_per_s": n / (sum(mean_stage.values()) * 1e-3) / 1e6,
+                    "window_bits": int(info[1]), "windows": int(info[2]), "stages_ms": mean_stage},
+            "ntt": {"ms": ntt_ms, "alg_GBps": ntt_gbs, "melem_per_s": n / (ntt_ms * 1e-3) / 1e6},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sweep(args, torch, b200zk, lib, dev) -> None:
+    """k = 16..26 table: MSM Mpts/s and NTT GB/s with inputs resident in HBM (1 GPU)."""
+    from b200zk.api import _ptr
+    stream = torch.cuda.Stream(device=dev)
+    st = C.c_void_p(stream.cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    peak = b200zk.modmul_peak(4096)
+    rows = []
+    b200zk.check(lib.b200zk_msm_profile(1))
+    for k in range(16, 27):
+        n = 1 << k
+        d_scal = torch.empty(n * 4, dtype=torch.int64, device=dev)
+        d_base = torch.empty(n * 8, dtype=torch.int64, device=dev)
+        d_pt = torch.zeros(12, dtype=torch.int64, device=dev)
+        b200zk.check(lib.b200zk_gen_scalars_dev(vp(d_scal), n, SEED_S + k, 0))
+        b200zk.check(lib.b200zk_gen_points_dev(vp(d_base), n, SEED_P + k, 0))
+        d_ntt = d_scal.clone()
+        omega = fr_limbs(omega_for(k))
+        reps = 5 if k <= 22 else 3
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                b200zk.check(lib.b200zk_msm_g1_dev_async(vp(d_scal), vp(d_base), n, vp(d_pt), st))
+                b200zk.check(lib.b200zk_ntt_dev(vp(d_ntt), n, 1, k, _ptr(omega), None, st))
+            torch.cuda.synchronize()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(stream)
+            for _ in range(reps):
+                b200zk.check(lib.b200zk_msm_g1_dev_async(vp(d_scal), vp(d_base), n, vp(d_pt), st))
+            e[1].record(stream)
+            for _ in range(reps):
+                b200zk.check(lib.b200zk_ntt_dev(vp(d_ntt), n, 1, k, _ptr(omega), None, st))
+            e[2].record(stream)
+            torch.cuda.synchronize()
+        msm_ms = e[0].elapsed_time(e[1]) / reps
+        ntt_ms = e[1].elapsed_time(e[2]) / reps
+        ms = (C.c_float * 9)()
+        info = (C.c_uint64 * 5)()
+        b200zk.check(lib.b200zk_msm_last_stages(ms, 9, info))
+        acc = 10.0 * info[3] / (ms[4] * 1e-3)
+        passes = max(1, -(-k // 9))
+        ntt_mm = n * (k / 2 + 2 * (passes - 1)) / (ntt_ms * 1e-3)
+        rows.append({"k": k, "msm_ms": msm_ms, "msm_mpts_per_s": n / msm_ms / 1e3, "c": int(info[1]),
+                     "accum_ms": ms[4], "accum_frac_of_modmul_peak": acc / peak,
+                     "ntt_ms": ntt_ms, "ntt_alg_GBps": ntt_alg_bytes(k) / ntt_ms / 1e6,
+                     "ntt_frac_of_modmul_peak": ntt_mm / peak})
+        del d_scal, d_base, d_ntt
+    print(json.dumps({"sweep": rows, "modmul_peak_G_per_s": peak / 1e9}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,12 @@ int b200zk_gen_points_dev(void* d_out, size_t n, uint64_t seed, size_t start);
 /* Register-resident Fq multiply chain on every SM; returns field multiplications / s.
  * This is the measured denominator of the MSM integer-pipe roofline. */
 int b200zk_modmul_peak(uint32_t iters, double* modmul_per_s_out);
+/* Per-stage CUDA-event timing of the MSM pipeline (recorded on the stream the kernels run
+ * on).  After a profiled MSM, b200zk_msm_last_stages fills ms_out[0..8] with the stage
+ * durations {hist, scan, scatter, sync, accumulate, combine, reduce, reduce-combine, fold}
+ * and info_out with {n, window bits c, windows, (bucket, point) pairs, chunk length}. */
+int b200zk_msm_profile(int enable);
+int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]);
 /* Number of kernels launched by this library since init (for bench.py gpu_launches). */
 uint64_t b200zk_kernel_launches(void);
 
