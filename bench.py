@@ -85,7 +85,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -93,9 +93,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def stop(self, t_begin: float = 0.0, t_end: float = 1e300) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -106,7 +106,12 @@ class ClockSampler:
         sm, mx, pw = [], [], []
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines if t_begin <= ts <= t_end + 0.15]
+        window = "timed region"
+        if not inside:  # region shorter than one sampling period: fall back to warm-up + timed region
+            inside = [ln for (_, ln) in self.lines]
+            window = "warm-up + timed region (timed region shorter than one nvidia-smi period)"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -118,7 +123,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -262,18 +268,19 @@ def main() -> None:
             if timed:
                 ntt_ev.append((e0, e1))
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step(False)
     barrier()
     b200zk.check(lib.b200zk_msm_profile(1))
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = b200zk.kernel_launches()
     stage_ms = []
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps):
         step(True)
@@ -283,9 +290,10 @@ def main() -> None:
         stage_ms.append(list(ms))
     ev1.record(stream)
     barrier()
+    t_end = time.perf_counter()
     launches = b200zk.kernel_launches() - launches0
     total_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     b200zk.check(lib.b200zk_msm_profile(0))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
