@@ -24,3 +24,10 @@ from .api import (  # noqa: F401
     modmul_peak,
     shutdown,
 )
+from .quotient import (  # noqa: F401,E402
+    DeviceColumn,
+    Evaluator,
+    FlatGraph,
+    LookupCommitted,
+    ProvingKeyCosets,
+)

@@ -67,6 +67,14 @@ def load() -> C.CDLL:
         "b200zk_msm_g1_dev": ([vp, vp, sz, vp, vp], C.c_int),
         "b200zk_msm_g1_dev_async": ([vp, vp, sz, vp, vp], C.c_int),
         "b200zk_g1_sum": ([vp, sz, vp], C.c_int),
+        "b200zk_dev_alloc": ([sz, u64p], C.c_int),
+        "b200zk_dev_free": ([u64], C.c_int),
+        "b200zk_dev_upload": ([u64, sz, vp, sz], C.c_int),
+        "b200zk_dev_download": ([u64, sz, vp, sz], C.c_int),
+        "b200zk_dev_ptr": ([u64], vp),
+        "b200zk_quotient_graph": ([vp, vp, u64, u64], C.c_int),
+        "b200zk_quotient_permutation": ([vp, u64, vp, vp, vp, u32, vp, u32, u32, u32, u64, u64, u64, vp, vp, vp], C.c_int),
+        "b200zk_quotient_lookup": ([vp, u64, u64, u64, u64, u64, u64, u64, u64], C.c_int),
         "b200zk_gen_scalars_dev": ([vp, sz, u64, sz], C.c_int),
         "b200zk_gen_points_dev": ([vp, sz, u64, sz], C.c_int),
         "b200zk_modmul_peak": ([u32, C.POINTER(C.c_double)], C.c_int),

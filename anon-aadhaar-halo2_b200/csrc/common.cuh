@@ -83,6 +83,10 @@ struct PinnedArena {
 
 struct NttTables;
 struct BaseTable;
+struct DevBuffer {
+    void* p = nullptr;
+    size_t n_elems = 0;
+};
 
 struct Context {
     bool ready = false;
@@ -96,11 +100,14 @@ struct Context {
     PinnedArena pinned;
     std::vector<NttTables*> ntt_tables;
     std::map<uint64_t, BaseTable*> bases;
+    std::map<uint64_t, DevBuffer> buffers;  // device-resident Fr columns (b200zk_dev_*)
+    Arena quot_graph, quot_ptrs;
     uint64_t next_handle = 1;
 };
 
 Context& ctx();
 void ensure_init();
+NttTables* ntt_get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStream_t s);
 
 inline Fr fr_from_limbs(const uint64_t* l) {
     Fr r;

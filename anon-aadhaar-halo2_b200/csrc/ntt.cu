@@ -15,20 +15,6 @@ static __global__ void fr_pow_table_kernel(Fr base, uint32_t mult, uint32_t coun
     st_fr(out + i, base.pow_u64((uint64_t)i * mult));
 }
 
-// Per-(omega, log_n) twiddle tables, built on the device once and cached.
-struct NttTables {
-    Fr omega;
-    uint32_t log_n;
-    int npass;
-    int bits[4];
-    Fr* tw_tile[NTT_MAX_B + 1];  // indexed by b
-    Fr* tw_lo;
-    Fr* tw_hi;
-    uint32_t tw_h;
-    Fr w8[3];
-    Fr* block;  // single allocation
-};
-
 static void plan_bits(uint32_t log_n, int& npass, int* bits) {
     npass = (int)((log_n + NTT_MAX_B - 1) / NTT_MAX_B);
     if (npass == 0) npass = 1;
@@ -36,7 +22,7 @@ static void plan_bits(uint32_t log_n, int& npass, int* bits) {
     for (int p = 0; p < npass; ++p) bits[p] = base + (p < rem ? 1 : 0);
 }
 
-static NttTables* get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStream_t s) {
+NttTables* ntt_get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStream_t s) {
     for (NttTables* t : c.ntt_tables)
         if (t->log_n == log_n && t->omega == omega) return t;
     ZK_REQUIRE(log_n >= 1 && log_n <= 28, "log_n out of range (1..28)");
@@ -134,7 +120,7 @@ template <bool FIRST> static void launch_pass_b(int b, const NttPassArgs& a, uns
 static void ntt_run(Context& c, const Fr* in, uint64_t in_stride, Fr* out, uint64_t out_stride, Fr* tmp,
                     size_t count, uint32_t log_n, const Fr& omega, const NttMods& mods, cudaStream_t s) {
     if (count == 0) return;
-    NttTables* t = get_tables(c, omega, log_n, s);
+    NttTables* t = ntt_get_tables(c, omega, log_n, s);
     const uint64_t n = (uint64_t)1 << log_n;
     const int P = t->npass;
     // destination of pass p (0-based); see DESIGN.md "NTT buffer rotation"

@@ -56,6 +56,20 @@ struct NttPassArgs {
     uint64_t out_batch_stride;
 };
 
+// Per-(omega, log_n) twiddle tables, built on the device once and cached (ntt.cu).
+struct NttTables {
+    Fr omega;
+    uint32_t log_n;
+    int npass;
+    int bits[4];
+    Fr* tw_tile[NTT_MAX_B + 1];  // indexed by b: (omega^(n / 2^b))^e
+    Fr* tw_lo;                   // omega^x, x < 2^tw_h
+    Fr* tw_hi;                   // omega^(y << tw_h)
+    uint32_t tw_h;
+    Fr w8[3];
+    Fr* block;  // single allocation
+};
+
 #if defined(__CUDACC__)
 
 __device__ __forceinline__ Fr ld_fr(const Fr* p) {

@@ -108,6 +108,71 @@ int b200zk_msm_g1_dev_async(const void* d_scalars, const void* d_bases, size_t n
  * best_multiexp applies to its per-chunk results; used to combine per-GPU partial MSMs. */
 int b200zk_g1_sum(const uint64_t* points_xyz, size_t count, uint64_t out_xyz[12]);
 
+/* ---- device-resident Fr columns -------------------------------------------------------- */
+/* The quotient evaluation reads hundreds of extended columns; they live in HBM and are
+ * addressed by handle.  Sizes and offsets are in field elements (32 bytes). */
+int b200zk_dev_alloc(size_t n_elems, uint64_t* handle_out);
+int b200zk_dev_free(uint64_t handle);
+int b200zk_dev_upload(uint64_t handle, size_t offset, const uint64_t* host, size_t n_elems);
+int b200zk_dev_download(uint64_t handle, size_t offset, uint64_t* host, size_t n_elems);
+/* Raw device pointer of a handle (NULL if unknown), for the *_dev entry points above. */
+void* b200zk_dev_ptr(uint64_t handle);
+
+/* ---- quotient: plonk::evaluation::Evaluator::evaluate_h ------------------------------ */
+/* Flat encoding of halo2_proofs/src/plonk/evaluation.rs `GraphEvaluator`.
+ * b200zk_src mirrors `ValueSource`: kind 0 Constant(a) 1 Intermediate(a) 2 Fixed(a, rot b)
+ * 3 Advice(a, rot b) 4 Instance(a, rot b) 5 Challenge(a) 6 Beta 7 Gamma 8 Theta 9 Y
+ * 10 PreviousValue; `b` indexes `rotations`.
+ * b200zk_calc mirrors `CalculationInfo`: op 0 Add(x,y) 1 Sub(x,y) 2 Mul(x,y) 3 Square(x)
+ * 4 Double(x) 5 Negate(x) 6 Horner(start = x, parts[parts_off..+parts_len], factor = y)
+ * 7 Store(x); the result goes to intermediates[target]. */
+typedef struct { uint32_t kind, a, b; } b200zk_src;
+typedef struct { uint32_t op, target; b200zk_src x, y; uint32_t parts_off, parts_len; } b200zk_calc;
+typedef struct {
+    const uint64_t* constants;  uint32_t n_constants;   /* n x 4 limbs */
+    const int32_t* rotations;   uint32_t n_rotations;
+    const b200zk_calc* calcs;   uint32_t n_calcs;
+    const b200zk_src* parts;    uint32_t n_parts;
+    uint32_t n_intermediates;
+} b200zk_graph;
+/* Everything `GraphEvaluator::evaluate` reads besides the graph: extended-domain column
+ * handles (each 2^ext_k elements), challenges (n x 4 limbs) and the four scalars. */
+typedef struct {
+    const uint64_t* fixed;     uint32_t n_fixed;       /* handles */
+    const uint64_t* advice;    uint32_t n_advice;
+    const uint64_t* instance;  uint32_t n_instance;
+    const uint64_t* challenges; uint32_t n_challenges;
+    uint64_t beta[4], gamma[4], theta[4], y[4];
+    uint32_t k, ext_k;
+} b200zk_quotient_env;
+
+/* out[idx] = graph.evaluate(idx, previous_value = previous[idx] or 0 when the handle is 0)
+ * for every idx of the extended domain; rotation r reads index
+ * (idx + r * 2^(ext_k - k)) mod 2^ext_k.  `out` may equal `previous` (the custom-gate
+ * loop of evaluate_h: values[idx] = custom_gates.evaluate(.., &values[idx], ..)). */
+int b200zk_quotient_graph(const b200zk_graph* graph, const b200zk_quotient_env* env, uint64_t previous_handle,
+                          uint64_t out_handle);
+
+/* The permutation-argument block of evaluate_h, folded into `values` in upstream's order:
+ * l_0 (1 - z_0); l_last (z_l^2 - z_l); l_0 (z_i - z_{i-1}(omega^last X)) for i > 0; then per
+ * set (z_i(omega X) prod(v + beta sigma + gamma) - z_i(X) prod(v + delta^j beta X + gamma)) * l_active.
+ * column_kind[j] in {2 fixed, 3 advice, 4 instance} and column_index[j] name permutation
+ * column j inside `env`; sigma[j] is pk.permutation.cosets[j]; products[i] the z_i cosets. */
+int b200zk_quotient_permutation(const b200zk_quotient_env* env, uint64_t values_handle,
+                                const uint32_t* column_kind, const uint32_t* column_index,
+                                const uint64_t* sigma_handles, uint32_t n_columns,
+                                const uint64_t* product_handles, uint32_t n_sets, uint32_t chunk_len,
+                                uint32_t blinding_factors, uint64_t l0_handle, uint64_t l_last_handle,
+                                uint64_t l_active_row_handle, const uint64_t extended_omega[4],
+                                const uint64_t zeta[4], const uint64_t delta[4]);
+
+/* One lookup argument's five constraints folded into `values`; `table_values` is the
+ * output of b200zk_quotient_graph on that lookup's graph with previous = 0. */
+int b200zk_quotient_lookup(const b200zk_quotient_env* env, uint64_t values_handle, uint64_t table_values_handle,
+                           uint64_t product_handle, uint64_t permuted_input_handle,
+                           uint64_t permuted_table_handle, uint64_t l0_handle, uint64_t l_last_handle,
+                           uint64_t l_active_row_handle);
+
 /* ---- synthetic inputs (benchmark / test support; oracle/bn254.py defines the streams) -- */
 int b200zk_gen_scalars_dev(void* d_out, size_t n, uint64_t seed, size_t start);
 int b200zk_gen_points_dev(void* d_out, size_t n, uint64_t seed, size_t start);
