@@ -180,8 +180,8 @@ class Evaluator:
         instance = self._extend(domain, instance_polys)
         env = self._env(domain, pk.fixed_cosets, advice, instance, challenges, beta, gamma, theta, y)
         values = DeviceColumn(domain.extended_len())
-        check(lib.b200zk_dev_upload(values.handle, 0, _ptr(np.zeros((domain.extended_len(), 4), np.uint64)),
-                                    domain.extended_len()))
+        zeros = np.zeros((domain.extended_len(), 4), np.uint64)   # domain.empty_extended()
+        check(lib.b200zk_dev_upload(values.handle, 0, _ptr(zeros), domain.extended_len()))
         g = self.custom_gates.as_c()
         check(lib.b200zk_quotient_graph(C.byref(g), C.byref(env), values.handle, values.handle))
         if len(permutation_products):
@@ -191,10 +191,11 @@ class Evaluator:
             idxs = np.array([i for (_, i) in pk.permutation_columns], dtype=np.uint32)
             sig = _handles(pk.permutation_cosets)
             ph = _handles(products)
+            zeta, delta = fr_limbs(FR_ZETA), fr_limbs(FR_DELTA)   # keep alive across the call
             check(lib.b200zk_quotient_permutation(
                 C.byref(env), values.handle, _ptr32(kinds), _ptr32(idxs), _ptr(sig), len(kinds), _ptr(ph), len(products),
                 pk.degree - 2, pk.blinding_factors, pk.l0.handle, pk.l_last.handle, pk.l_active_row.handle,
-                _ptr(domain.extended_omega), _ptr(fr_limbs(FR_ZETA)), _ptr(fr_limbs(FR_DELTA))))
+                _ptr(domain.extended_omega), _ptr(zeta), _ptr(delta)))
             for c in products:
                 c.free()
         for n, lk in enumerate(lookups):
