@@ -44,7 +44,8 @@ class EnvC(C.Structure):
                 ("instance", C.c_void_p), ("n_instance", C.c_uint32),
                 ("challenges", C.c_void_p), ("n_challenges", C.c_uint32),
                 ("beta", C.c_uint64 * 4), ("gamma", C.c_uint64 * 4), ("theta", C.c_uint64 * 4),
-                ("y", C.c_uint64 * 4), ("k", C.c_uint32), ("ext_k", C.c_uint32)]
+                ("y", C.c_uint64 * 4), ("k", C.c_uint32), ("ext_k", C.c_uint32),
+                ("range_begin", C.c_uint64), ("range_len", C.c_uint64)]
 
 
 assert C.sizeof(Src) == 12 and C.sizeof(Calc) == 40
@@ -143,7 +144,7 @@ class Evaluator:
         self.lookups = list(lookups)
         self._lib = load()
 
-    def _env(self, domain, fixed, advice, instance, challenges, beta, gamma, theta, y):
+    def _env(self, domain, fixed, advice, instance, challenges, beta, gamma, theta, y, idx_range=None):
         keep = [_handles(fixed), _handles(advice), _handles(instance),
                 np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4)]
         env = EnvC()
@@ -154,6 +155,7 @@ class Evaluator:
         for name, v in (("beta", beta), ("gamma", gamma), ("theta", theta), ("y", y)):
             getattr(env, name)[:] = [int(x) for x in np.asarray(v, dtype=np.uint64)]
         env.k, env.ext_k = domain.k, domain.extended_k
+        env.range_begin, env.range_len = (idx_range[0], idx_range[1] - idx_range[0]) if idx_range else (0, 0)
         env._keep = keep
         return env
 
@@ -171,14 +173,16 @@ class Evaluator:
         return out
 
     def evaluate_h(self, domain: EvaluationDomain, pk: ProvingKeyCosets, advice_polys, instance_polys, challenges,
-                   y, beta, gamma, theta, lookups=(), permutation_products=()) -> np.ndarray:
+                   y, beta, gamma, theta, lookups=(), permutation_products=(), idx_range=None) -> np.ndarray:
         """One circuit instance of `Evaluator::evaluate_h`.  advice / instance / lookup /
         permutation-product polynomials are host arrays in coefficient form, as
-        `create_proof` holds them; returns the extended-domain numerator (host array)."""
+        `create_proof` holds them; returns the extended-domain numerator (host array).
+        With ``idx_range=(begin, end)`` only that slice of the extended domain is evaluated
+        (one rank's share of a multi-GPU evaluation) and only that slice is returned."""
         lib = self._lib
         advice = self._extend(domain, advice_polys)
         instance = self._extend(domain, instance_polys)
-        env = self._env(domain, pk.fixed_cosets, advice, instance, challenges, beta, gamma, theta, y)
+        env = self._env(domain, pk.fixed_cosets, advice, instance, challenges, beta, gamma, theta, y, idx_range)
         values = DeviceColumn(domain.extended_len())
         zeros = np.zeros((domain.extended_len(), 4), np.uint64)   # domain.empty_extended()
         check(lib.b200zk_dev_upload(values.handle, 0, _ptr(zeros), domain.extended_len()))
@@ -208,6 +212,8 @@ class Evaluator:
             for c in (prod, pin, ptab, table):
                 c.free()
         out = values.to_host()
+        if idx_range:
+            out = out[idx_range[0]:idx_range[1]].copy()
         for c in advice + instance + [values]:
             c.free()
         return out

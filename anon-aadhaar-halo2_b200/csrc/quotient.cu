@@ -42,15 +42,17 @@ struct GraphDev {
     const Fr* challenges;
     Fr beta, gamma, theta, y;
     uint32_t log_size, log_rot_scale;
+    uint32_t begin, count;  // index range evaluated by this launch
     const Fr* previous;  // may be null
     Fr* out;
 };
 
 template <int MAXI>
 __global__ void __launch_bounds__(128) quotient_graph_kernel(const __grid_constant__ GraphDev G) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tix = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t size = 1u << G.log_size;
-    if (idx >= size) return;
+    if (tix >= G.count) return;
+    const uint32_t idx = G.begin + tix;
     Fr inter[MAXI];
     uint32_t rots[QMAX_ROT];
     for (uint32_t r = 0; r < G.n_rotations; ++r) {
@@ -112,13 +114,15 @@ struct PermDev {
     uint32_t n_columns, n_sets, chunk_len;
     int32_t last_rotation;
     uint32_t log_size, log_rot_scale;
+    uint32_t begin, count;
     Fr beta, gamma, y, delta_start, delta;
 };
 
 __global__ void __launch_bounds__(128) quotient_permutation_kernel(const __grid_constant__ PermDev P) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tix = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t size = 1u << P.log_size;
-    if (idx >= size) return;
+    if (tix >= P.count) return;
+    const uint32_t idx = P.begin + tix;
     const uint32_t rs = 1u << P.log_rot_scale;
     const uint32_t r_next = (idx + rs) & (size - 1u);
     const uint32_t r_last = (uint32_t)((int32_t)idx + P.last_rotation * (int32_t)rs) & (size - 1u);
@@ -169,13 +173,15 @@ struct LookupDev {
     const Fr* l_last;
     const Fr* l_active;
     uint32_t log_size, log_rot_scale;
+    uint32_t begin, count;
     Fr beta, gamma, y;
 };
 
 __global__ void __launch_bounds__(128) quotient_lookup_kernel(const __grid_constant__ LookupDev L) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tix = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t size = 1u << L.log_size;
-    if (idx >= size) return;
+    if (tix >= L.count) return;
+    const uint32_t idx = L.begin + tix;
     const uint32_t rs = 1u << L.log_rot_scale;
     const uint32_t r_next = (idx + rs) & (size - 1u);
     const uint32_t r_prev = (idx - rs) & (size - 1u);
@@ -231,6 +237,14 @@ static void check_env(const b200zk_quotient_env* env) {
     ZK_REQUIRE(env->n_advice == 0 || env->advice, "null advice handles");
     ZK_REQUIRE(env->n_instance == 0 || env->instance, "null instance handles");
     ZK_REQUIRE(env->n_challenges == 0 || env->challenges, "null challenges");
+    const uint64_t size = (uint64_t)1 << env->ext_k;
+    ZK_REQUIRE(env->range_begin <= size && env->range_len <= size - env->range_begin, "index range outside the domain");
+}
+
+static void env_range(const b200zk_quotient_env* env, uint32_t& begin, uint32_t& count) {
+    const uint64_t size = (uint64_t)1 << env->ext_k;
+    begin = (uint32_t)env->range_begin;
+    count = (uint32_t)(env->range_len ? env->range_len : size - env->range_begin);
 }
 
 }  // namespace zk
@@ -372,7 +386,8 @@ int b200zk_quotient_graph(const b200zk_graph* g, const b200zk_quotient_env* env,
         G.log_rot_scale = env->ext_k - env->k;
         G.previous = previous_handle ? col_ptr(c, previous_handle, size, "previous values") : nullptr;
         G.out = (Fr*)buffer_of(c, out_handle, size, "output values").p;
-        const unsigned blocks = (unsigned)((size + 127) / 128);
+        env_range(env, G.begin, G.count);
+        const unsigned blocks = (unsigned)((G.count + 127) / 128);
         if (g->n_intermediates <= 64) quotient_graph_kernel<64><<<blocks, 128, 0, s>>>(G);
         else if (g->n_intermediates <= 256) quotient_graph_kernel<256><<<blocks, 128, 0, s>>>(G);
         else quotient_graph_kernel<1024><<<blocks, 128, 0, s>>>(G);
@@ -436,7 +451,8 @@ int b200zk_quotient_permutation(const b200zk_quotient_env* env, uint64_t values_
         P.y = fr_from_limbs(env->y);
         P.delta_start = P.beta * fr_from_limbs(zeta);
         P.delta = fr_from_limbs(delta);
-        quotient_permutation_kernel<<<(unsigned)((size + 127) / 128), 128, 0, s>>>(P);
+        env_range(env, P.begin, P.count);
+        quotient_permutation_kernel<<<(unsigned)((P.count + 127) / 128), 128, 0, s>>>(P);
         ZK_LAUNCH_CHECK();
         ZK_CUDA(cudaStreamSynchronize(s));
     });
@@ -466,7 +482,8 @@ int b200zk_quotient_lookup(const b200zk_quotient_env* env, uint64_t values_handl
         L.beta = fr_from_limbs(env->beta);
         L.gamma = fr_from_limbs(env->gamma);
         L.y = fr_from_limbs(env->y);
-        quotient_lookup_kernel<<<(unsigned)((size + 127) / 128), 128, 0, s>>>(L);
+        env_range(env, L.begin, L.count);
+        quotient_lookup_kernel<<<(unsigned)((L.count + 127) / 128), 128, 0, s>>>(L);
         ZK_LAUNCH_CHECK();
         ZK_CUDA(cudaStreamSynchronize(s));
     });

@@ -144,6 +144,10 @@ typedef struct {
     const uint64_t* challenges; uint32_t n_challenges;
     uint64_t beta[4], gamma[4], theta[4], y[4];
     uint32_t k, ext_k;
+    /* Multi-GPU sharding of the extended domain: only indices [range_begin, range_begin +
+     * range_len) are evaluated and written (range_len = 0: the whole domain).  Inputs stay
+     * full columns because rotations reach outside the range. */
+    uint64_t range_begin, range_len;
 } b200zk_quotient_env;
 
 /* out[idx] = graph.evaluate(idx, previous_value = previous[idx] or 0 when the handle is 0)
