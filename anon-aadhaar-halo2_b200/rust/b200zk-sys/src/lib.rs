@@ -1,0 +1,79 @@
+//! Raw FFI declarations of include/b200zk.h (hand-written; keep in sync with the header —
+//! tests/test_abi.py checks the header against the shared library's exports).
+//!
+//! NOT COMPILED HERE: no Rust toolchain exists in this image.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct b200zk_src { pub kind: u32, pub a: u32, pub b: u32 }
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct b200zk_calc { pub op: u32, pub target: u32, pub x: b200zk_src, pub y: b200zk_src, pub parts_off: u32, pub parts_len: u32 }
+
+#[repr(C)]
+pub struct b200zk_graph {
+    pub constants: *const u64, pub n_constants: u32,
+    pub rotations: *const i32, pub n_rotations: u32,
+    pub calcs: *const b200zk_calc, pub n_calcs: u32,
+    pub parts: *const b200zk_src, pub n_parts: u32,
+    pub n_intermediates: u32,
+}
+
+#[repr(C)]
+pub struct b200zk_quotient_env {
+    pub fixed: *const u64, pub n_fixed: u32,
+    pub advice: *const u64, pub n_advice: u32,
+    pub instance: *const u64, pub n_instance: u32,
+    pub challenges: *const u64, pub n_challenges: u32,
+    pub beta: [u64; 4], pub gamma: [u64; 4], pub theta: [u64; 4], pub y: [u64; 4],
+    pub k: u32, pub ext_k: u32,
+    pub range_begin: u64, pub range_len: u64,
+}
+
+extern "C" {
+    pub fn b200zk_init(device: c_int) -> c_int;
+    pub fn b200zk_shutdown() -> c_int;
+    pub fn b200zk_last_error() -> *const c_char;
+    pub fn b200zk_abi_version() -> u32;
+
+    pub fn b200zk_ntt(a: *mut u64, log_n: u32, omega: *const u64) -> c_int;
+    pub fn b200zk_intt(a: *mut u64, log_n: u32, omega_inv: *const u64, divisor: *const u64) -> c_int;
+    pub fn b200zk_coeff_to_extended(input: *const u64, k: u32, out: *mut u64, ext_k: u32, extended_omega: *const u64, zeta: *const u64) -> c_int;
+    pub fn b200zk_extended_to_coeff(a: *const u64, ext_k: u32, extended_omega_inv: *const u64, extended_ifft_divisor: *const u64, zeta: *const u64, out: *mut u64, keep: usize) -> c_int;
+    pub fn b200zk_divide_by_vanishing(h: *mut u64, ext_k: u32, t_evaluations: *const u64, t_len: u32) -> c_int;
+    pub fn b200zk_ntt_many(a: *mut u64, stride: usize, count: usize, log_n: u32, omega: *const u64) -> c_int;
+    pub fn b200zk_intt_many(a: *mut u64, stride: usize, count: usize, log_n: u32, omega_inv: *const u64, divisor: *const u64) -> c_int;
+    pub fn b200zk_coeff_to_extended_many(input: *const u64, in_stride: usize, out: *mut u64, out_stride: usize, count: usize, k: u32, ext_k: u32, extended_omega: *const u64, zeta: *const u64) -> c_int;
+    pub fn b200zk_ntt_dev(d_a: *mut c_void, stride: usize, count: usize, log_n: u32, omega: *const u64, divisor_or_null: *const u64, stream: *mut c_void) -> c_int;
+    pub fn b200zk_coeff_to_extended_dev(d_in: *const c_void, in_stride: usize, d_out: *mut c_void, out_stride: usize, count: usize, k: u32, ext_k: u32, extended_omega: *const u64, zeta: *const u64, stream: *mut c_void) -> c_int;
+    pub fn b200zk_extended_to_coeff_dev(d_a: *const c_void, ext_k: u32, extended_omega_inv: *const u64, extended_ifft_divisor: *const u64, zeta: *const u64, d_t_evaluations_or_null: *const c_void, t_len: u32, d_out: *mut c_void, keep: usize, stream: *mut c_void) -> c_int;
+
+    pub fn b200zk_msm_g1(scalars: *const u64, bases: *const u64, n: usize, out_xyz: *mut u64) -> c_int;
+    pub fn b200zk_bases_register(bases: *const u64, n: usize, handle_out: *mut u64) -> c_int;
+    pub fn b200zk_bases_evict(handle: u64) -> c_int;
+    pub fn b200zk_msm_g1_registered(handle: u64, scalars: *const u64, n: usize, out_xyz: *mut u64) -> c_int;
+    pub fn b200zk_msm_g1_dev(d_scalars: *const c_void, d_bases: *const c_void, n: usize, out_xyz: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn b200zk_msm_g1_dev_async(d_scalars: *const c_void, d_bases: *const c_void, n: usize, d_out_xyz: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn b200zk_g1_sum(points_xyz: *const u64, count: usize, out_xyz: *mut u64) -> c_int;
+
+    pub fn b200zk_dev_alloc(n_elems: usize, handle_out: *mut u64) -> c_int;
+    pub fn b200zk_dev_free(handle: u64) -> c_int;
+    pub fn b200zk_dev_upload(handle: u64, offset: usize, host: *const u64, n_elems: usize) -> c_int;
+    pub fn b200zk_dev_download(handle: u64, offset: usize, host: *mut u64, n_elems: usize) -> c_int;
+    pub fn b200zk_dev_ptr(handle: u64) -> *mut c_void;
+
+    pub fn b200zk_quotient_graph(graph: *const b200zk_graph, env: *const b200zk_quotient_env, previous_handle: u64, out_handle: u64) -> c_int;
+    pub fn b200zk_quotient_permutation(env: *const b200zk_quotient_env, values_handle: u64, column_kind: *const u32, column_index: *const u32, sigma_handles: *const u64, n_columns: u32, product_handles: *const u64, n_sets: u32, chunk_len: u32, blinding_factors: u32, l0_handle: u64, l_last_handle: u64, l_active_row_handle: u64, extended_omega: *const u64, zeta: *const u64, delta: *const u64) -> c_int;
+    pub fn b200zk_quotient_lookup(env: *const b200zk_quotient_env, values_handle: u64, table_values_handle: u64, product_handle: u64, permuted_input_handle: u64, permuted_table_handle: u64, l0_handle: u64, l_last_handle: u64, l_active_row_handle: u64) -> c_int;
+}
+
+/// Panic with the library's message, as upstream's infallible functions would on a failed assert.
+pub fn check(rc: c_int) {
+    if rc != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(b200zk_last_error()) }.to_string_lossy().into_owned();
+        panic!("b200zk: {msg}");
+    }
+}

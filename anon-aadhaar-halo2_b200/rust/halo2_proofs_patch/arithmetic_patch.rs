@@ -1,0 +1,117 @@
+// Replacement bodies for halo2_proofs/src/arithmetic.rs and halo2_proofs/src/poly/domain.rs
+// @ v2023_01_20.  SOURCE ONLY: no Rust toolchain exists in this image.
+//
+// The bn256 types are plain `[u64; 4]` Montgomery limbs (`Fr`, `Fq`), `G1Affine { x, y }` and
+// `G1 { x, y, z }`; the const assertions below make the layout assumption explicit.
+use std::any::TypeId;
+use std::mem::{size_of, transmute_copy};
+
+use b200zk_sys as ffi;
+use halo2curves::bn256::{Fr, G1Affine, G1};
+
+const _: () = assert!(size_of::<Fr>() == 32 && size_of::<G1Affine>() == 64 && size_of::<G1>() == 96);
+
+/// `arithmetic::best_multiexp` — signature unchanged.
+pub fn best_multiexp<C: CurveAffine>(coeffs: &[C::Scalar], bases: &[C]) -> C::Curve {
+    assert_eq!(coeffs.len(), bases.len());
+    if TypeId::of::<C>() == TypeId::of::<G1Affine>() {
+        let mut out = [0u64; 12];
+        ffi::check(unsafe {
+            ffi::b200zk_msm_g1(coeffs.as_ptr() as *const u64, bases.as_ptr() as *const u64, coeffs.len(), out.as_mut_ptr())
+        });
+        // SAFETY: C::Curve == G1 here; [u64; 12] is its in-memory representation.
+        return unsafe { transmute_copy::<[u64; 12], C::Curve>(&out) };
+    }
+    upstream::best_multiexp(coeffs, bases) // unchanged generic CPU path for other curves
+}
+
+/// `arithmetic::best_fft` — signature unchanged.
+pub fn best_fft<G: Group>(a: &mut [G], omega: G::Scalar, log_n: u32) {
+    assert_eq!(a.len(), 1 << log_n);
+    if TypeId::of::<G>() == TypeId::of::<Fr>() {
+        ffi::check(unsafe { ffi::b200zk_ntt(a.as_mut_ptr() as *mut u64, log_n, &omega as *const _ as *const u64) });
+        return;
+    }
+    upstream::best_fft(a, omega, log_n)
+}
+
+impl<G: Group> EvaluationDomain<G> {
+    /// `EvaluationDomain::lagrange_to_coeff` — ifft + divisor in one device call.
+    pub fn lagrange_to_coeff(&self, mut a: Polynomial<G, LagrangeCoeff>) -> Polynomial<G, Coeff> {
+        assert_eq!(a.values.len(), 1 << self.k);
+        if TypeId::of::<G>() == TypeId::of::<Fr>() {
+            ffi::check(unsafe {
+                ffi::b200zk_intt(a.values.as_mut_ptr() as *mut u64, self.k,
+                                 &self.omega_inv as *const _ as *const u64, &self.ifft_divisor as *const _ as *const u64)
+            });
+        } else {
+            Self::ifft(&mut a.values, self.omega_inv, self.k, self.ifft_divisor);
+        }
+        Polynomial { values: a.values, _marker: PhantomData }
+    }
+
+    /// `EvaluationDomain::coeff_to_extended` — zeta shift, zero padding and NTT fused.
+    pub fn coeff_to_extended(&self, a: Polynomial<G, Coeff>) -> Polynomial<G, ExtendedLagrangeCoeff> {
+        assert_eq!(a.values.len(), 1 << self.k);
+        if TypeId::of::<G>() == TypeId::of::<Fr>() {
+            let mut out = vec![G::group_zero(); self.extended_len()];
+            ffi::check(unsafe {
+                ffi::b200zk_coeff_to_extended(a.values.as_ptr() as *const u64, self.k, out.as_mut_ptr() as *mut u64,
+                                              self.extended_k, &self.extended_omega as *const _ as *const u64,
+                                              &self.g_coset as *const _ as *const u64)
+            });
+            return Polynomial { values: out, _marker: PhantomData };
+        }
+        upstream::coeff_to_extended(self, a)
+    }
+
+    /// `EvaluationDomain::extended_to_coeff` — inverse NTT, un-shift and truncation fused.
+    pub fn extended_to_coeff(&self, a: Polynomial<G, ExtendedLagrangeCoeff>) -> Vec<G> {
+        assert_eq!(a.values.len(), self.extended_len());
+        if TypeId::of::<G>() == TypeId::of::<Fr>() {
+            let keep = (self.n * self.quotient_poly_degree) as usize;
+            let mut out = vec![G::group_zero(); keep];
+            ffi::check(unsafe {
+                ffi::b200zk_extended_to_coeff(a.values.as_ptr() as *const u64, self.extended_k,
+                                              &self.extended_omega_inv as *const _ as *const u64,
+                                              &self.extended_ifft_divisor as *const _ as *const u64,
+                                              &self.g_coset as *const _ as *const u64, out.as_mut_ptr() as *mut u64, keep)
+            });
+            return out;
+        }
+        upstream::extended_to_coeff(self, a)
+    }
+
+    /// `EvaluationDomain::divide_by_vanishing_poly`.
+    pub fn divide_by_vanishing_poly(&self, mut a: Polynomial<G, ExtendedLagrangeCoeff>) -> Polynomial<G, ExtendedLagrangeCoeff> {
+        assert_eq!(a.values.len(), self.extended_len());
+        if TypeId::of::<G>() == TypeId::of::<Fr>() {
+            ffi::check(unsafe {
+                ffi::b200zk_divide_by_vanishing(a.values.as_mut_ptr() as *mut u64, self.extended_k,
+                                                self.t_evaluations.as_ptr() as *const u64, self.t_evaluations.len() as u32)
+            });
+            return a;
+        }
+        upstream::divide_by_vanishing_poly(self, a)
+    }
+}
+
+// poly/kzg/commitment.rs: ParamsKZG<Bn256> gains two private fields holding the handles returned by
+// b200zk_bases_register(g) / (g_lagrange) at construction (`setup`, `read`, `downsize` re-register),
+// and a Drop impl calling b200zk_bases_evict.  Bodies:
+//
+//   fn commit(&self, poly: &Polynomial<Fr, Coeff>, _: Blind<Fr>) -> G1 {
+//       let mut out = [0u64; 12];
+//       ffi::check(unsafe { ffi::b200zk_msm_g1_registered(self.g_handle, poly.as_ptr() as *const u64, poly.len(), out.as_mut_ptr()) });
+//       unsafe { transmute::<[u64; 12], G1>(out) }
+//   }
+//   fn commit_lagrange(..)  — same with self.g_lagrange_handle.
+//
+// plonk/evaluation.rs: Evaluator::evaluate_h flattens self.custom_gates / self.lookups[n] into
+// b200zk_graph (ValueSource / Calculation discriminants are the `kind` / `op` numbers documented in
+// include/b200zk.h), keeps pk.fixed_cosets, pk.l0 / l_last / l_active_row and pk.permutation.cosets
+// resident through b200zk_dev_alloc + b200zk_dev_upload at keygen time, extends advice / instance /
+// lookup / permutation-product polynomials with b200zk_coeff_to_extended_dev into device columns, and
+// calls b200zk_quotient_graph, b200zk_quotient_permutation and b200zk_quotient_lookup in upstream's
+// loop order; the result is downloaded into `values` (or kept resident for vanishing::construct,
+// which then calls b200zk_extended_to_coeff_dev with t_evaluations fused).
