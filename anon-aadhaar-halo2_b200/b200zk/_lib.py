@@ -62,6 +62,9 @@ def load() -> C.CDLL:
         "b200zk_extended_to_coeff_dev": ([vp, u32, vp, vp, vp, vp, u32, vp, sz, vp], C.c_int),
         "b200zk_msm_g1": ([vp, vp, sz, vp], C.c_int),
         "b200zk_bases_register": ([vp, sz, u64p], C.c_int),
+        "b200zk_bases_register_ex": ([vp, sz, C.c_int, u64p], C.c_int),
+        "b200zk_msm_g1_registered_many": ([u64, vp, sz, sz, sz, vp], C.c_int),
+        "b200zk_msm_g1_registered_dev": ([u64, vp, sz, sz, sz, vp, vp], C.c_int),
         "b200zk_bases_evict": ([u64], C.c_int),
         "b200zk_msm_g1_registered": ([u64, vp, sz, vp], C.c_int),
         "b200zk_msm_g1_dev": ([vp, vp, sz, vp, vp], C.c_int),
@@ -80,6 +83,7 @@ def load() -> C.CDLL:
         "b200zk_modmul_peak": ([u32, C.POINTER(C.c_double)], C.c_int),
         "b200zk_kernel_launches": ([], u64),
         "b200zk_msm_profile": ([C.c_int], C.c_int),
+        "b200zk_msm_tune": ([u32], C.c_int),
         "b200zk_msm_last_stages": ([C.POINTER(C.c_float), C.c_int, u64p], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():

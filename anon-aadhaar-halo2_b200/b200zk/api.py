@@ -195,19 +195,36 @@ class ParamsKZG:
     of the params) and evicted when the object is dropped.
     """
 
-    def __init__(self, g: np.ndarray, g_lagrange: np.ndarray):
+    def __init__(self, g: np.ndarray, g_lagrange: np.ndarray, precompute_windows: bool = True):
         _check_vec(g, 8, "g")
         _check_vec(g_lagrange, 8, "g_lagrange")
         assert g.shape[0] == g_lagrange.shape[0]
         self.n = g.shape[0]
         self._lib = load()
+        self._pre = 1 if precompute_windows else 0
         self._h_g = self._register(g)
         self._h_gl = self._register(g_lagrange)
 
     def _register(self, bases: np.ndarray) -> int:
         h = C.c_uint64(0)
-        check(self._lib.b200zk_bases_register(_ptr(bases), bases.shape[0], C.byref(h)))
+        check(self._lib.b200zk_bases_register_ex(_ptr(bases), bases.shape[0], self._pre, C.byref(h)))
         return h.value
+
+    def _msm_many(self, handle: int, polys: np.ndarray) -> np.ndarray:
+        assert polys.dtype == np.uint64 and polys.ndim == 3 and polys.shape[2] == 4
+        assert polys.shape[1] <= self.n
+        polys = np.ascontiguousarray(polys)
+        out = np.zeros((polys.shape[0], 12), dtype=np.uint64)
+        check(self._lib.b200zk_msm_g1_registered_many(handle, _ptr(polys), polys.shape[1], polys.shape[0],
+                                                      polys.shape[1], _ptr(out)))
+        return out
+
+    def commit_many(self, polys: np.ndarray) -> np.ndarray:
+        """`polys.iter().map(|p| params.commit(p, _))` in one device pipeline; polys is (count, len, 4)."""
+        return self._msm_many(self._h_g, polys)
+
+    def commit_lagrange_many(self, polys: np.ndarray) -> np.ndarray:
+        return self._msm_many(self._h_gl, polys)
 
     def _msm(self, handle: int, poly: np.ndarray) -> np.ndarray:
         _check_vec(poly, 4, "poly")

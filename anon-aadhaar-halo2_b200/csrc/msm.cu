@@ -32,14 +32,20 @@
 
 namespace zk {
 
+// Registered bases (ParamsKZG::g / g_lagrange): the points, and optionally the table
+// T[w * n + i] = 2^(c*w) * P_i in affine form, which lets every window share one bucket set
+// (no per-window reduction, no doubling chain at the end).
 struct BaseTable {
     G1Affine* d = nullptr;
     size_t n = 0;
+    G1Affine* table = nullptr;
+    uint32_t c = 0, nwin = 0;
 };
 
 void msm_release_bases(Context& c) {
     for (auto& kv : c.bases) {
         cudaFree(kv.second->d);
+        if (kv.second->table) cudaFree(kv.second->table);
         delete kv.second;
     }
     c.bases.clear();
@@ -100,16 +106,42 @@ __device__ __forceinline__ void for_each_digit(const uint32_t* s, uint32_t c, ui
 }
 
 // ------------------------------------------------------------ 1. digits + histogram
-__global__ void msm_hist_kernel(const Fr* __restrict__ scalars, size_t n, uint32_t c, uint32_t nwin,
-                                uint32_t* __restrict__ hist) {
+// Also stores the signed digits window-major (digits[(col * nwin + w) * n + i], 0 = dropped)
+// so that the scatter can run one window at a time: all blocks in flight then touch one
+// window's counters (2^(c-1) * 4 B) and one window's slice of the sorted list (<= n * 4 B),
+// which stay in the 126 MB L2 instead of spraying 4-byte stores over every window at once.
+// blockIdx.y = column of a batch.  key = (col * key_windows + (key_windows > 1 ? w : 0)) * nb
+// + |digit| - 1: with a precomputed table all windows share one bucket set (key_windows = 1).
+__global__ void msm_hist_kernel(const Fr* __restrict__ scalars, size_t scalar_stride, size_t n, uint32_t c,
+                                uint32_t nwin, uint32_t key_windows, uint32_t* __restrict__ hist,
+                                int32_t* __restrict__ digits) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Fr s = ldg_fr(scalars + i).from_mont();
+    const uint32_t col = blockIdx.y;
+    const Fr s = ldg_fr(scalars + (size_t)col * scalar_stride + i).from_mont();
     const uint32_t nb = 1u << (c - 1);
-    for_each_digit(s.l, c, nwin, [&](uint32_t w, int32_t d) {
-        const uint32_t mag = (uint32_t)(d < 0 ? -d : d);
-        atomicAdd(hist + (size_t)w * nb + (mag - 1), 1u);
-    });
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t mask = (1u << c) - 1u;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < nwin; ++w) {
+        const uint32_t o = w * c;
+        const uint32_t limb = o >> 5, sh = o & 31u;
+        uint32_t raw = 0;
+        if (limb < 8) {
+            raw = s.l[limb] >> sh;
+            if (sh + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh);
+        }
+        const uint32_t d = (raw & mask) + carry;
+        int32_t sd;
+        if (d > half) { sd = (int32_t)d - (int32_t)(1u << c); carry = 1; }
+        else { sd = (int32_t)d; carry = 0; }
+        digits[((size_t)col * nwin + w) * n + i] = sd;
+        if (sd != 0) {
+            const uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
+            const size_t group = (size_t)col * key_windows + (key_windows > 1 ? w : 0);
+            atomicAdd(hist + group * nb + (mag - 1), 1u);
+        }
+    }
 }
 
 // ------------------------------------------------------------------- 2. prefix scan
@@ -195,18 +227,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __rest
 }
 
 // --------------------------------------------------------------------- 3. scatter
-__global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, size_t n, uint32_t c, uint32_t nwin,
-                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+// grid = (ceil(n / 256), columns * windows): blocks of one window are scheduled together.
+// The stored value is the index of the point to add: i, or w * table_stride + i into the
+// precomputed table, with the sign of the digit in bit 31.
+__global__ void msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n, uint32_t c, uint32_t nwin,
+                                   uint32_t key_windows, uint32_t table_stride, uint32_t* __restrict__ cursor,
+                                   uint32_t* __restrict__ sorted) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Fr s = ldg_fr(scalars + i).from_mont();
+    const uint32_t cw = blockIdx.y;             // col * nwin + w
+    const int32_t d = __ldg(digits + (size_t)cw * n + i);
+    if (d == 0) return;
+    const uint32_t col = cw / nwin, w = cw - col * nwin;
     const uint32_t nb = 1u << (c - 1);
-    for_each_digit(s.l, c, nwin, [&](uint32_t w, int32_t d) {
-        const uint32_t mag = (uint32_t)(d < 0 ? -d : d);
-        const uint32_t pos = atomicAdd(cursor + (size_t)w * nb + (mag - 1), 1u);
-        sorted[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
-    });
+    const uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+    const size_t group = (size_t)col * key_windows + (key_windows > 1 ? w : 0);
+    const uint32_t pos = atomicAdd(cursor + group * nb + (mag - 1), 1u);
+    sorted[pos] = ((uint32_t)i + w * table_stride) | (d < 0 ? 0x80000000u : 0u);
 }
+
+constexpr uint32_t MSM_PAD_KEY = 0xffffffffu;   // padding lane (real keys are < 2^31)
 
 // ------------------------------------------------------- 4. bucket accumulation, level 0
 // start[0..K] are the bucket offsets (start[K] = npairs).  Thread t owns pairs
@@ -261,48 +301,114 @@ __global__ void __launch_bounds__(128) msm_accum_kernel(const G1Affine* __restri
         if (negate) p.y = p.y.neg();
         acc.add_affine(p);
     }
+    if (run_end == end) {
+        // the chunk ends exactly where its last run ends: nothing continues into the next
+        // chunk, so the run is complete on its right side like the interior ones
+        st_xyzz(buckets + key, acc);
+        acc = G1Xyzz::identity();   // hand up (key, identity): keys stay dense and sorted
+    }
     carry_key[t] = key;
     st_xyzz(carry_pt + t, acc);
 }
 
 // ------------------------------------------------------ 4b. keyed reduction, level >= 1
-// Entries (keys[i], pts[i]) with non-decreasing keys.  Thread t owns entries
-// [t*L, (t+1)*L); closed runs are *added* to buckets[key]; the last run goes up a level,
-// unless this is the final level (one thread), which adds it too.
+// Entries (keys[i], pts[i]) with non-decreasing keys.  A run of equal keys is *closed* where
+// it ends (the next entry has another key, or there is none); exactly one thread per level
+// sees a given key close, and only that thread adds the run's sum into buckets[key].  Open
+// last runs are handed up as (key, partial); closed ones hand up (key, identity) so the next
+// level's keys stay dense and sorted.
+//
+// Sequential form (throughput regime): thread t owns entries [t*L, (t+1)*L).
 __global__ void __launch_bounds__(128) msm_combine_kernel(const uint32_t* __restrict__ keys, const G1Xyzz* __restrict__ pts,
                                                           uint32_t count, uint32_t L, G1Xyzz* __restrict__ buckets,
                                                           uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt,
-                                                          uint32_t nthreads, uint32_t final_level) {
+                                                          uint32_t nthreads) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
     const uint32_t begin = t * L;
     const uint32_t end = min(begin + L, count);
     uint32_t key = keys[begin];
     G1Xyzz acc = G1Xyzz::identity();
+    auto flush = [&]() {
+        if (!acc.is_identity()) {
+            G1Xyzz b = ld_xyzz(buckets + key);
+            b.add(acc);
+            st_xyzz(buckets + key, b);
+        }
+    };
 #pragma unroll 1
     for (uint32_t i = begin; i < end; ++i) {
         const uint32_t k = keys[i];
         if (k != key) {
-            if (!acc.is_identity()) {
-                G1Xyzz b = ld_xyzz(buckets + key);
-                b.add(acc);
-                st_xyzz(buckets + key, b);
-            }
+            flush();
             acc = G1Xyzz::identity();
             key = k;
         }
         G1Xyzz p = ld_xyzz(pts + i);
         acc.add(p);
     }
-    if (final_level) {
-        if (!acc.is_identity()) {
-            G1Xyzz b = ld_xyzz(buckets + key);
-            b.add(acc);
-            st_xyzz(buckets + key, b);
-        }
-    } else {
-        carry_key[t] = key;
-        st_xyzz(carry_pt + t, acc);
+    if (end == count || keys[end] != key) {
+        flush();
+        acc = G1Xyzz::identity();
+    }
+    carry_key[t] = key;
+    st_xyzz(carry_pt + t, acc);
+}
+
+__device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& v, uint32_t d) {
+    G1Xyzz r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], d);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], d);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], d);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], d);
+    }
+    return r;
+}
+
+// Warp form (latency regime): one entry per lane, segmented shuffle reduction by key in five
+// steps; each warp hands up one entry, so a level shrinks the list 32x for the latency of
+// five point additions.  When count <= 32 the single warp closes everything.
+__global__ void __launch_bounds__(128) msm_combine_warp_kernel(const uint32_t* __restrict__ keys,
+                                                               const G1Xyzz* __restrict__ pts, uint32_t count,
+                                                               G1Xyzz* __restrict__ buckets,
+                                                               uint32_t* __restrict__ carry_key,
+                                                               G1Xyzz* __restrict__ carry_pt) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = gid >> 5;
+    const uint32_t base = warp << 5;
+    if (base >= count) return;                       // whole warp beyond the list
+    const bool valid = gid < count;
+    const uint32_t key = valid ? keys[gid] : MSM_PAD_KEY;
+    G1Xyzz v = valid ? ld_xyzz(pts + gid) : G1Xyzz::identity();
+#pragma unroll 1
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
+        const G1Xyzz o = shfl_down_xyzz(v, d);
+        if (lane + d < 32 && ok == key) v.add(o);
+    }
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (prev != key);
+    const uint32_t last_lane = min(31u, count - base - 1u);
+    const uint32_t k_last = __shfl_sync(0xffffffffu, key, last_lane);
+    if (!(head && valid)) return;
+    const bool reaches_end = (key == k_last);
+    const bool open = reaches_end && (base + 32 < count) && (keys[base + 32] == key);
+    if (open) {
+        carry_key[warp] = key;
+        st_xyzz(carry_pt + warp, v);
+        return;
+    }
+    if (!v.is_identity()) {
+        G1Xyzz b = ld_xyzz(buckets + key);
+        b.add(v);
+        st_xyzz(buckets + key, b);
+    }
+    if (reaches_end) {
+        carry_key[warp] = key;
+        st_xyzz(carry_pt + warp, G1Xyzz::identity());
     }
 }
 
@@ -341,16 +447,43 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const G1Xyzz* __restric
 }
 
 // ----------------------------------------------------------------------- 6. fold
-__global__ void msm_fold_kernel(const G1Xyzz* __restrict__ win, uint32_t nwin, uint32_t c, G1Jacobian* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// One thread per column of the batch: Horner over that column's windows.
+__global__ void msm_fold_kernel(const G1Xyzz* __restrict__ win, uint32_t nwin, uint32_t c, uint32_t count,
+                                G1Jacobian* out) {
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= count) return;
     G1Xyzz acc = G1Xyzz::identity();
     for (int w = (int)nwin - 1; w >= 0; --w) {
         if (!acc.is_identity())
             for (uint32_t i = 0; i < c; ++i) acc = acc.dbl();
-        G1Xyzz x = ld_xyzz(win + w);
+        G1Xyzz x = ld_xyzz(win + (size_t)col * nwin + w);
         acc.add(x);
     }
-    *out = acc.to_jacobian();
+    out[col] = acc.to_jacobian();
+}
+
+// T[w * n + i] = 2^(c*w) * P_i, affine.  One thread per point walks the doubling chain and
+// normalises each multiple with a field inversion (one-off cost at registration).
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const G1Affine* __restrict__ bases, size_t n, uint32_t c,
+                                                             uint32_t nwin, G1Affine* __restrict__ table) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p;
+    p.x = ldg_fq(&bases[i].x);
+    p.y = ldg_fq(&bases[i].y);
+    st_fq(&table[i].x, p.x);
+    st_fq(&table[i].y, p.y);
+    for (uint32_t w = 1; w < nwin; ++w) {
+        if (!p.is_identity()) {
+            G1Xyzz a = G1Xyzz::double_affine(p);
+            for (uint32_t k = 1; k < c; ++k) a = a.dbl();
+            G1Jacobian j = a.to_jacobian_normalized();
+            p.x = j.x;
+            p.y = j.y;
+        }
+        st_fq(&table[(size_t)w * n + i].x, p.x);
+        st_fq(&table[(size_t)w * n + i].y, p.y);
+    }
 }
 
 __global__ void g1_sum_kernel(const G1Jacobian* __restrict__ pts, uint32_t count, G1Jacobian* out) {
@@ -375,6 +508,7 @@ enum MsmStage { MSM_ST_HIST = 0, MSM_ST_SCAN, MSM_ST_SCATTER, MSM_ST_SYNC, MSM_S
 struct MsmInfo { uint64_t n; uint32_t c, nwin, npairs, chunk; };
 static MsmInfo g_msm_info = {0, 0, 0, 0, 0};
 static bool g_msm_profile = false;
+static uint32_t g_msm_max_chunk = 128;   // tunable (b200zk_msm_tune)
 static cudaEvent_t g_msm_ev[MSM_ST_COUNT];
 static bool g_msm_ev_made = false, g_msm_ev_valid[MSM_ST_COUNT];
 static cudaStream_t g_msm_ev_stream = nullptr;
@@ -398,13 +532,14 @@ struct StageTimer {
     }
 };
 
-static uint32_t choose_window(size_t n) {
-    // minimise 10*n*W (mixed adds) + 30*W*2^(c-1) (two full adds per bucket + slack)
+// minimise 10*n*W (mixed adds) + 30*G*2^(c-1) (two full adds per bucket + slack), where G
+// is the number of bucket sets: W without a precomputed table, 1 with one.
+static uint32_t choose_window(size_t n, bool shared_buckets) {
     double best = 1e300;
     uint32_t bc = 4;
     for (uint32_t c = 4; c <= 23; ++c) {
         const double W = (255 + c - 1) / c;
-        const double cost = 10.0 * (double)n * W + 30.0 * W * (double)(1u << (c - 1));
+        const double cost = 10.0 * (double)n * W + 30.0 * (shared_buckets ? 1.0 : W) * (double)(1u << (c - 1));
         if (cost < best) { best = cost; bc = c; }
     }
     return bc;
@@ -412,63 +547,112 @@ static uint32_t choose_window(size_t n) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct MsmPlan {
-    uint32_t c, nwin, nb, nkeys;
+struct MsmPre {
+    const G1Affine* table;
+    size_t n_reg;
+    uint32_t c, nwin;
 };
 
 // Launch the keyed-reduction levels on (keys, pts)[count] until everything has been
-// added into `buckets`.  `scratch` provides the ping-pong carry arrays.
-static void run_combine_levels(uint32_t* keysA, G1Xyzz* ptsA, uint32_t* keysB, G1Xyzz* ptsB, uint32_t count,
-                               G1Xyzz* buckets, cudaStream_t s) {
-    const uint32_t L = 16;
-    while (true) {
-        const bool final_level = count <= 24;
-        const uint32_t Lc = final_level ? count : L;
-        const uint32_t nthreads = (count + Lc - 1) / Lc;
-        msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, count, Lc, buckets, keysB, ptsB,
-                                                                  nthreads, final_level ? 1u : 0u);
-        ZK_LAUNCH_CHECK();
-        if (final_level) break;
+// added into `buckets`.  Small inputs use short chunks: the cost of a level is the latency
+// of L dependent point additions, not throughput.
+static void run_combine_levels(Context& c, uint32_t* keysA, G1Xyzz* ptsA, uint32_t* keysB, G1Xyzz* ptsB,
+                               uint32_t count, G1Xyzz* buckets, cudaStream_t s) {
+    while (count > 0) {
+        if (count > 32768u) {
+            // throughput regime: sequential chunks, one addition per entry
+            const uint32_t L = count > (uint32_t)c.sm_count * 4096u ? 16u : 4u;
+            const uint32_t nthreads = (count + L - 1) / L;
+            msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, count, L, buckets, keysB, ptsB,
+                                                                      nthreads);
+            ZK_LAUNCH_CHECK();
+            count = nthreads;
+        } else {
+            const uint32_t nwarps = (count + 31) / 32;
+            msm_combine_warp_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, count, buckets, keysB, ptsB);
+            ZK_LAUNCH_CHECK();
+            if (nwarps == 1) break;
+            count = nwarps;
+        }
         std::swap(keysA, keysB);
         std::swap(ptsA, ptsB);
-        count = nthreads;
     }
 }
 
-// d_out: device G1Jacobian.  All inputs device-resident.
-static void msm_device(Context& c, const Fr* d_scalars, const G1Affine* d_bases, size_t n, G1Jacobian* d_out,
-                       cudaStream_t s) {
+// Sum `per_group` consecutive partials of each group: grid (nsplit, groups), 256 threads;
+// thread j adds its strided share, then a shared-memory tree.  out[group * nsplit + split].
+__global__ void __launch_bounds__(256) msm_group_sum_kernel(const G1Xyzz* __restrict__ pts, uint32_t per_group,
+                                                            uint32_t nsplit, G1Xyzz* __restrict__ out) {
+    extern __shared__ uint4 gs_smem[];
+    G1Xyzz* sh = reinterpret_cast<G1Xyzz*>(gs_smem);
+    const uint32_t group = blockIdx.y, split = blockIdx.x;
+    const uint32_t span = (per_group + nsplit - 1) / nsplit;
+    const uint32_t lo = split * span, hi = min(lo + span, per_group);
+    const G1Xyzz* base = pts + (size_t)group * per_group;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) {
+        G1Xyzz p = ld_xyzz(base + i);
+        acc.add(p);
+    }
+    st_xyzz(sh + threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t stride = 128; stride > 0; stride >>= 1) {
+        if (threadIdx.x < stride) {
+            G1Xyzz a = ld_xyzz(sh + threadIdx.x);
+            G1Xyzz b = ld_xyzz(sh + threadIdx.x + stride);
+            a.add(b);
+            st_xyzz(sh + threadIdx.x, a);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_xyzz(out + (size_t)group * nsplit + split, ld_xyzz(sh));
+}
+
+// `count` MSMs over the same n bases: column j uses scalars d_scalars + j * scalar_stride and
+// writes d_out[j].  All inputs device-resident.  `pre` (optional) is a per-window table.
+static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, size_t count,
+                       const G1Affine* d_bases, size_t n, const MsmPre* pre, G1Jacobian* d_out, cudaStream_t s) {
     ZK_REQUIRE(n < ((size_t)1 << 28), "MSM size must be below 2^28 points");
+    if (count == 0) return;
     if (n == 0) {
         G1Jacobian id;
         id.x = Fq::zero(); id.y = Fq::one(); id.z = Fq::zero();
-        ZK_CUDA(cudaMemcpyAsync(d_out, &id, sizeof id, cudaMemcpyHostToDevice, s));
+        for (size_t j = 0; j < count; ++j)
+            ZK_CUDA(cudaMemcpyAsync(d_out + j, &id, sizeof id, cudaMemcpyHostToDevice, s));
         ZK_CUDA(cudaStreamSynchronize(s));
         return;
     }
-    MsmPlan P;
-    P.c = choose_window(n);
-    P.nwin = (255 + P.c - 1) / P.c;
-    P.nb = 1u << (P.c - 1);
-    P.nkeys = P.nwin * P.nb;
-    const size_t max_pairs = n * P.nwin;
-    ZK_REQUIRE(max_pairs < ((size_t)1 << 32), "MSM too large for 32-bit pair offsets");
+    const uint32_t cbits = pre ? pre->c : choose_window(n, false);
+    const uint32_t nwin = (255 + cbits - 1) / cbits;
+    const uint32_t key_windows = pre ? 1u : nwin;
+    const uint32_t nb = 1u << (cbits - 1);
+    const size_t groups = count * key_windows;            // bucket sets
+    const size_t nkeys_sz = groups * nb;
+    const size_t max_pairs = n * nwin * count;
+    ZK_REQUIRE(max_pairs < ((size_t)1 << 32) && nkeys_sz < ((size_t)1 << 31), "MSM batch too large for 32-bit offsets");
+    ZK_REQUIRE(count * nwin <= 65535, "MSM batch has too many (column, window) pairs");
+    if (pre) ZK_REQUIRE(pre->n_reg * (size_t)nwin < ((size_t)1 << 31), "precomputed table too large for 31-bit indices");
+    const uint32_t nkeys = (uint32_t)nkeys_sz;
 
     // ---- carve the sort arena (sizes known up front)
-    const uint32_t scan_blocks = (uint32_t)((P.nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    const uint32_t seglen = 32;
-    const uint32_t segs_per_win = (P.nb + seglen - 1) / seglen;
-    const size_t red_entries = (size_t)segs_per_win * P.nwin;
+    const uint32_t scan_blocks = (uint32_t)((nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    // segment length of the bucket reduction: enough segments to fill the machine, short
+    // enough that 2 * seglen dependent additions stay cheap
+    uint32_t seglen = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(4, nkeys / ((uint64_t)c.sm_count * 256)));
+    if (seglen > nb) seglen = nb;
+    const uint32_t segs_per_group = (nb + seglen - 1) / seglen;
+    const size_t red_entries = (size_t)segs_per_group * groups;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_hist = carve(((size_t)P.nkeys + 1) * 4);
-    const size_t o_start = carve(((size_t)P.nkeys + 1) * 4);
-    const size_t o_cursor = carve(((size_t)P.nkeys + 1) * 4);
+    const size_t o_hist = carve(((size_t)nkeys + 1) * 4);
+    const size_t o_start = carve(((size_t)nkeys + 1) * 4);
+    const size_t o_cursor = carve(((size_t)nkeys + 1) * 4);
     const size_t o_bsum = carve(((size_t)scan_blocks + 1) * 4);
     const size_t o_total = carve(256);
     const size_t o_sorted = carve(max_pairs * 4);
-    const size_t o_buckets = carve((size_t)P.nkeys * sizeof(G1Xyzz));
-    const size_t o_win = carve((size_t)P.nwin * sizeof(G1Xyzz));
+    const size_t o_digits = carve(max_pairs * 4);
+    const size_t o_buckets = carve((size_t)nkeys * sizeof(G1Xyzz));
+    const size_t o_win = carve(groups * sizeof(G1Xyzz));
     char* base = (char*)c.msm_work.get(off);
     uint32_t* hist = (uint32_t*)(base + o_hist);
     uint32_t* start = (uint32_t*)(base + o_start);
@@ -476,73 +660,89 @@ static void msm_device(Context& c, const Fr* d_scalars, const G1Affine* d_bases,
     uint32_t* bsum = (uint32_t*)(base + o_bsum);
     uint32_t* total = (uint32_t*)(base + o_total);
     uint32_t* sorted = (uint32_t*)(base + o_sorted);
+    int32_t* digits = (int32_t*)(base + o_digits);
     G1Xyzz* buckets = (G1Xyzz*)(base + o_buckets);
     G1Xyzz* win = (G1Xyzz*)(base + o_win);
 
     StageTimer T(c, s);
     // ---- 1-3: sort (bucket, point) pairs
-    ZK_CUDA(cudaMemsetAsync(hist, 0, ((size_t)P.nkeys + 1) * 4, s));
-    ZK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)P.nkeys * sizeof(G1Xyzz), s));
-    ZK_CUDA(cudaMemsetAsync(win, 0, (size_t)P.nwin * sizeof(G1Xyzz), s));
+    ZK_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nkeys + 1) * 4, s));
+    ZK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nkeys * sizeof(G1Xyzz), s));
+    ZK_CUDA(cudaMemsetAsync(win, 0, groups * sizeof(G1Xyzz), s));
     const unsigned sblocks = (unsigned)((n + 255) / 256);
     T.mark(MSM_ST_HIST);
-    msm_hist_kernel<<<sblocks, 256, 0, s>>>(d_scalars, n, P.c, P.nwin, hist);
+    msm_hist_kernel<<<dim3(sblocks, (unsigned)count), 256, 0, s>>>(d_scalars, scalar_stride, n, cbits, nwin,
+                                                                    key_windows, hist, digits);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SCAN);
-    scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(hist, start, bsum, P.nkeys);
+    scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(hist, start, bsum, nkeys);
     ZK_LAUNCH_CHECK();
     scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(bsum, scan_blocks, total);
     ZK_LAUNCH_CHECK();
-    scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, P.nkeys, total);
+    scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, nkeys, total);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SCATTER);
-    msm_scatter_kernel<<<sblocks, 256, 0, s>>>(d_scalars, n, P.c, P.nwin, cursor, sorted);
+    msm_scatter_kernel<<<dim3(sblocks, (unsigned)(count * nwin)), 256, 0, s>>>(
+        digits, n, cbits, nwin, key_windows, pre ? (uint32_t)pre->n_reg : 0u, cursor, sorted);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SYNC);
     uint32_t npairs = 0;
     ZK_CUDA(cudaMemcpyAsync(&npairs, total, 4, cudaMemcpyDeviceToHost, s));
     ZK_CUDA(cudaStreamSynchronize(s));
 
-    // chunk length: keep >= ~1024 threads per SM in flight, between 4 and 32 pairs each
-    const uint32_t L = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(4, npairs / ((uint64_t)c.sm_count * 1024)));
+    // chunk length: keep >= ~4096 threads per SM queued, between 4 and 128 pairs each (longer
+    // chunks mean fewer open runs handed to the keyed-reduction levels)
+    const uint32_t L = (uint32_t)std::min<uint64_t>(g_msm_max_chunk, std::max<uint64_t>(4, npairs / ((uint64_t)c.sm_count * 4096)));
     const uint32_t nthreads0 = (npairs + L - 1) / L;
     // ---- carve the carry arena now that the pair count is known
     const size_t carry_cap = std::max<size_t>(std::max<size_t>(nthreads0, red_entries), 64);
     off = 0;
     const size_t o_keyA = carve(carry_cap * 4);
     const size_t o_ptA = carve(carry_cap * sizeof(G1Xyzz));
-    const size_t o_keyB = carve((carry_cap / 16 + 64) * 4);
-    const size_t o_ptB = carve((carry_cap / 16 + 64) * sizeof(G1Xyzz));
+    const size_t capB = std::max<size_t>(carry_cap / 4 + 64, groups * 64);
+    const size_t o_keyB = carve(capB * 4);
+    const size_t o_ptB = carve(capB * sizeof(G1Xyzz));
     char* cbase = (char*)c.msm_carry.get(off);
     uint32_t* keyA = (uint32_t*)(cbase + o_keyA);
     G1Xyzz* ptA = (G1Xyzz*)(cbase + o_ptA);
     uint32_t* keyB = (uint32_t*)(cbase + o_keyB);
     G1Xyzz* ptB = (G1Xyzz*)(cbase + o_ptB);
-    g_msm_info.n = n; g_msm_info.c = P.c; g_msm_info.nwin = P.nwin; g_msm_info.npairs = npairs; g_msm_info.chunk = L;
+    g_msm_info.n = n * count; g_msm_info.c = cbits; g_msm_info.nwin = nwin; g_msm_info.npairs = npairs; g_msm_info.chunk = L;
 
     // ---- 4: accumulate
     T.mark(MSM_ST_ACCUM);
     if (npairs > 0) {
-        msm_accum_kernel<<<(nthreads0 + 127) / 128, 128, 0, s>>>(d_bases, sorted, start, P.nkeys, npairs, L, buckets,
-                                                                 keyA, ptA, nthreads0);
+        msm_accum_kernel<<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start, nkeys,
+                                                                 npairs, L, buckets, keyA, ptA, nthreads0);
         ZK_LAUNCH_CHECK();
         T.mark(MSM_ST_COMBINE);
-        run_combine_levels(keyA, ptA, keyB, ptB, nthreads0, buckets, s);
+        run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, buckets, s);
     }
 
-    // ---- 5: per-window running sums, then keyed reduction with key = window
+    // ---- 5: per-bucket-set running sums, then keyed reduction with key = bucket set
     T.mark(MSM_ST_REDUCE);
     {
         const uint32_t nthreads = (uint32_t)red_entries;
-        msm_reduce_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(buckets, P.nb, seglen, segs_per_win, P.nwin, keyA,
-                                                                 ptA);
+        msm_reduce_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(buckets, nb, seglen, segs_per_group, (uint32_t)groups,
+                                                                 keyA, ptA);
         ZK_LAUNCH_CHECK();
         T.mark(MSM_ST_REDUCE_COMBINE);
-        run_combine_levels(keyA, ptA, keyB, ptB, nthreads, win, s);
+        // per bucket set: sum its segment partials (block tree, two stages when long)
+        const uint32_t nsplit = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, segs_per_group / 2048));
+        const int smem = 256 * sizeof(G1Xyzz);
+        if (nsplit == 1) {
+            msm_group_sum_kernel<<<dim3(1, (unsigned)groups), 256, smem, s>>>(ptA, segs_per_group, 1, win);
+            ZK_LAUNCH_CHECK();
+        } else {
+            msm_group_sum_kernel<<<dim3(nsplit, (unsigned)groups), 256, smem, s>>>(ptA, segs_per_group, nsplit, ptB);
+            ZK_LAUNCH_CHECK();
+            msm_group_sum_kernel<<<dim3(1, (unsigned)groups), 256, smem, s>>>(ptB, nsplit, 1, win);
+            ZK_LAUNCH_CHECK();
+        }
     }
     T.mark(MSM_ST_FOLD);
-    // ---- 6: fold the windows
-    msm_fold_kernel<<<1, 32, 0, s>>>(win, P.nwin, P.c, d_out);
+    // ---- 6: fold each column's windows (a single one with a precomputed table)
+    msm_fold_kernel<<<(unsigned)((count + 31) / 32), 32, 0, s>>>(win, key_windows, cbits, (uint32_t)count, d_out);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_END);
 }
@@ -572,26 +772,45 @@ int b200zk_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint
             ZK_CUDA(cudaMemcpyAsync(ds, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
             ZK_CUDA(cudaMemcpyAsync(db, bases, n * sizeof(G1Affine), cudaMemcpyHostToDevice, s));
         }
-        msm_device(c, ds, db, n, dout, s);
+        msm_device(c, ds, n, 1, db, n, nullptr, dout, s);
         copy_point_out(c, dout, out_xyz, s);
     });
 }
 
+static void register_bases(const uint64_t* bases, size_t n, int precompute, uint64_t* handle_out) {
+    ZK_REQUIRE(handle_out && (n == 0 || bases), "null argument");
+    ensure_init();
+    Context& c = ctx();
+    BaseTable* t = new BaseTable();
+    t->n = n;
+    if (n) {
+        ZK_CUDA(cudaMalloc(&t->d, n * sizeof(G1Affine)));
+        ZK_CUDA(cudaMemcpy(t->d, bases, n * sizeof(G1Affine), cudaMemcpyHostToDevice));
+    }
+    if (n && precompute) {
+        t->c = choose_window(n, true);
+        t->nwin = (255 + t->c - 1) / t->c;
+        const size_t bytes = n * (size_t)t->nwin * sizeof(G1Affine);
+        size_t free_b = 0, total_b = 0;
+        ZK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (n * (size_t)t->nwin < ((size_t)1 << 31) && bytes < free_b / 2) {
+            ZK_CUDA(cudaMalloc(&t->table, bytes));
+            msm_precompute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(t->d, n, t->c, t->nwin, t->table);
+            ZK_LAUNCH_CHECK();
+            ZK_CUDA(cudaStreamSynchronize(c.stream));
+        }  // otherwise: plain registered bases (generic pipeline)
+    }
+    const uint64_t h = c.next_handle++;
+    c.bases[h] = t;
+    *handle_out = h;
+}
+
 int b200zk_bases_register(const uint64_t* bases, size_t n, uint64_t* handle_out) {
-    return guarded([&] {
-        ZK_REQUIRE(handle_out && (n == 0 || bases), "null argument");
-        ensure_init();
-        Context& c = ctx();
-        BaseTable* t = new BaseTable();
-        t->n = n;
-        if (n) {
-            ZK_CUDA(cudaMalloc(&t->d, n * sizeof(G1Affine)));
-            ZK_CUDA(cudaMemcpy(t->d, bases, n * sizeof(G1Affine), cudaMemcpyHostToDevice));
-        }
-        const uint64_t h = c.next_handle++;
-        c.bases[h] = t;
-        *handle_out = h;
-    });
+    return guarded([&] { register_bases(bases, n, 1, handle_out); });
+}
+
+int b200zk_bases_register_ex(const uint64_t* bases, size_t n, int precompute_windows, uint64_t* handle_out) {
+    return guarded([&] { register_bases(bases, n, precompute_windows, handle_out); });
 }
 
 int b200zk_bases_evict(uint64_t handle) {
@@ -604,25 +823,58 @@ int b200zk_bases_evict(uint64_t handle) {
             cudaStreamSynchronize(c.stream);
         }
         cudaFree(it->second->d);
+        if (it->second->table) cudaFree(it->second->table);
         delete it->second;
         c.bases.erase(it);
     });
 }
 
+static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stride, size_t count, size_t n,
+                           uint64_t* out_xyz) {
+    ZK_REQUIRE(out_xyz && (n == 0 || scalars), "null argument");
+    ZK_REQUIRE(count <= 1 || stride >= n, "batch stride smaller than the column");
+    ensure_init();
+    Context& c = ctx();
+    auto it = c.bases.find(handle);
+    ZK_REQUIRE(it != c.bases.end(), "unknown bases handle");
+    BaseTable* t = it->second;
+    ZK_REQUIRE(n <= t->n, "more scalars than registered bases");
+    if (count == 0) return;
+    cudaStream_t s = c.stream;
+    Fr* ds = (Fr*)c.msm_scalars.get(std::max<size_t>(n * count, 1) * sizeof(Fr));
+    G1Jacobian* dout = (G1Jacobian*)c.misc.get(count * sizeof(G1Jacobian));
+    if (n)
+        ZK_CUDA(cudaMemcpy2DAsync(ds, n * sizeof(Fr), scalars, stride * sizeof(Fr), n * sizeof(Fr), count,
+                                  cudaMemcpyHostToDevice, s));
+    MsmPre pre{t->table, t->n, t->c, t->nwin};
+    msm_device(c, ds, n, count, t->d, n, t->table ? &pre : nullptr, dout, s);
+    ZK_CUDA(cudaMemcpyAsync(out_xyz, dout, count * sizeof(G1Jacobian), cudaMemcpyDeviceToHost, s));
+    ZK_CUDA(cudaStreamSynchronize(s));
+}
+
 int b200zk_msm_g1_registered(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]) {
+    return guarded([&] { msm_registered(handle, scalars, n, 1, n, out_xyz); });
+}
+
+int b200zk_msm_g1_registered_many(uint64_t handle, const uint64_t* scalars, size_t stride, size_t count, size_t n,
+                                  uint64_t* out_xyz) {
+    return guarded([&] { msm_registered(handle, scalars, stride, count, n, out_xyz); });
+}
+
+int b200zk_msm_g1_registered_dev(uint64_t handle, const void* d_scalars, size_t stride, size_t count, size_t n,
+                                 void* d_out_xyz, void* stream) {
     return guarded([&] {
-        ZK_REQUIRE(out_xyz && (n == 0 || scalars), "null argument");
+        ZK_REQUIRE(d_out_xyz && (n == 0 || d_scalars), "null argument");
+        ZK_REQUIRE(count <= 1 || stride >= n, "batch stride smaller than the column");
         ensure_init();
         Context& c = ctx();
         auto it = c.bases.find(handle);
         ZK_REQUIRE(it != c.bases.end(), "unknown bases handle");
-        ZK_REQUIRE(n <= it->second->n, "more scalars than registered bases");
-        cudaStream_t s = c.stream;
-        Fr* ds = (Fr*)c.msm_scalars.get(std::max<size_t>(n, 1) * sizeof(Fr));
-        G1Jacobian* dout = (G1Jacobian*)c.misc.get(sizeof(G1Jacobian));
-        if (n) ZK_CUDA(cudaMemcpyAsync(ds, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
-        msm_device(c, ds, it->second->d, n, dout, s);
-        copy_point_out(c, dout, out_xyz, s);
+        BaseTable* t = it->second;
+        ZK_REQUIRE(n <= t->n, "more scalars than registered bases");
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        MsmPre pre{t->table, t->n, t->c, t->nwin};
+        msm_device(c, (const Fr*)d_scalars, stride, count, t->d, n, t->table ? &pre : nullptr, (G1Jacobian*)d_out_xyz, s);
     });
 }
 
@@ -633,7 +885,7 @@ int b200zk_msm_g1_dev(const void* d_scalars, const void* d_bases, size_t n, uint
         Context& c = ctx();
         cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
         G1Jacobian* dout = (G1Jacobian*)c.misc.get(sizeof(G1Jacobian));
-        msm_device(c, (const Fr*)d_scalars, (const G1Affine*)d_bases, n, dout, s);
+        msm_device(c, (const Fr*)d_scalars, n, 1, (const G1Affine*)d_bases, n, nullptr, dout, s);
         copy_point_out(c, dout, out_xyz, s);
     });
 }
@@ -644,7 +896,14 @@ int b200zk_msm_g1_dev_async(const void* d_scalars, const void* d_bases, size_t n
         ensure_init();
         Context& c = ctx();
         cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
-        msm_device(c, (const Fr*)d_scalars, (const G1Affine*)d_bases, n, (G1Jacobian*)d_out_xyz, s);
+        msm_device(c, (const Fr*)d_scalars, n, 1, (const G1Affine*)d_bases, n, nullptr, (G1Jacobian*)d_out_xyz, s);
+    });
+}
+
+int b200zk_msm_tune(uint32_t max_chunk) {
+    return guarded([&] {
+        ZK_REQUIRE(max_chunk >= 4 && max_chunk <= 4096, "max_chunk out of range");
+        g_msm_max_chunk = max_chunk;
     });
 }
 

@@ -95,8 +95,22 @@ int b200zk_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint
  * `commit(poly)` == msm_g1_registered(handle(g), poly, len);
  * `commit_lagrange(poly)` == msm_g1_registered(handle(g_lagrange), poly, len). */
 int b200zk_bases_register(const uint64_t* bases, size_t n, uint64_t* handle_out);
+/* Same with control over the per-window table T[w][i] = 2^(c*w) * bases[i] that registration
+ * builds by default (W x the memory of the bases; every window then shares one bucket set and
+ * the final doubling chain disappears — the win for the prover's 2^15..2^17 commitments).
+ * precompute_windows = 0 keeps only the points. */
+int b200zk_bases_register_ex(const uint64_t* bases, size_t n, int precompute_windows, uint64_t* handle_out);
 int b200zk_bases_evict(uint64_t handle);
 int b200zk_msm_g1_registered(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]);
+/* `count` commitments against the same registered bases in one pipeline: column j is
+ * scalars + j * stride (n scalars each), result j at out_xyz + 12 * j.  This is the batched
+ * entry point behind create_proof's `advice.iter().map(|p| params.commit_lagrange(p))`. */
+int b200zk_msm_g1_registered_many(uint64_t handle, const uint64_t* scalars, size_t stride, size_t count, size_t n,
+                                  uint64_t* out_xyz);
+/* Device-resident scalars and results (count x 12 limbs at d_out_xyz), asynchronous on `stream`
+ * apart from one internal synchronisation. */
+int b200zk_msm_g1_registered_dev(uint64_t handle, const void* d_scalars, size_t stride, size_t count, size_t n,
+                                 void* d_out_xyz, void* stream);
 
 /* Device-resident form: d_scalars / d_bases are device pointers; result (12 limbs) is
  * written to host memory `out_xyz` after the stream is synchronised. */
@@ -190,6 +204,8 @@ int b200zk_modmul_peak(uint32_t iters, double* modmul_per_s_out);
  * durations {hist, scan, scatter, sync, accumulate, combine, reduce, reduce-combine, fold}
  * and info_out with {n, window bits c, windows, (bucket, point) pairs, chunk length}. */
 int b200zk_msm_profile(int enable);
+/* Tuning knob (benchmarks only): longest chunk of sorted pairs one thread accumulates. */
+int b200zk_msm_tune(uint32_t max_chunk);
 int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]);
 /* Number of kernels launched by this library since init (for bench.py gpu_launches). */
 uint64_t b200zk_kernel_launches(void);

@@ -112,3 +112,37 @@ def test_msm_full_size_linearity(zk, k):
         acc += si * ti
     scalar = acc % bn.R * rinv % bn.R                          # scalars are Montgomery representatives
     assert jac_affine(out) == bn.g1_mul(bn.G1_GEN, scalar)
+
+
+@pytest.mark.parametrize("precompute", [True, False])
+def test_params_kzg_window_table_and_batch(zk, precompute):
+    """Registered bases with / without the per-window table, single and batched commits,
+    including scalars that exercise every exceptional addition."""
+    n = 1 << 11
+    g, gl = co.gen_points(51, n), co.gen_points(52, n)
+    g[7] = g[6]                                   # repeated base
+    g[9] = 0                                      # identity base
+    params = zk.ParamsKZG(g, gl, precompute_windows=precompute)
+    cols = co.gen_scalars(53, 5 * n).reshape(5, n, 4).copy()
+    cols[1] = bn.fr_array_from_canonical([1] * n)                       # all ones
+    cols[2] = bn.fr_array_from_canonical([bn.R - 1] * n)                # all r-1
+    cols[3][np.arange(n) % 7 != 0] = 0                                  # sparse
+    cols[4] = bn.fr_array_from_canonical([(3 * i) % 4096 for i in range(n)])   # small witnesses
+    exp = [jac_affine(co.best_multiexp(cols[j], g)) for j in range(5)]
+    assert [jac_affine(params.commit(cols[j])) for j in range(5)] == exp
+    assert [jac_affine(p) for p in params.commit_many(cols)] == exp
+    expl = [jac_affine(co.best_multiexp(cols[j][:1500], gl[:1500])) for j in range(5)]
+    assert [jac_affine(p) for p in params.commit_lagrange_many(np.ascontiguousarray(cols[:, :1500]))] == expl
+    params.close()
+
+
+def test_commit_many_prover_shape(zk):
+    """The RSA-SHA256 shape of the reference (k = 15, src/lib.rs:444): a batch of advice
+    columns committed against g_lagrange in one pipeline."""
+    n, cnt = 1 << 15, 6
+    gl = co.gen_points(61, n)
+    params = zk.ParamsKZG(gl, gl)
+    cols = co.gen_scalars(62, cnt * n).reshape(cnt, n, 4)
+    got = [jac_affine(p) for p in params.commit_lagrange_many(cols)]
+    assert got == [jac_affine(co.best_multiexp(cols[j], gl)) for j in range(cnt)]
+    params.close()
