@@ -83,7 +83,7 @@ def load() -> C.CDLL:
         "b200zk_modmul_peak": ([u32, C.POINTER(C.c_double)], C.c_int),
         "b200zk_kernel_launches": ([], u64),
         "b200zk_msm_profile": ([C.c_int], C.c_int),
-        "b200zk_msm_tune": ([u32], C.c_int),
+        "b200zk_msm_tune": ([u32, u32, u32], C.c_int),
         "b200zk_msm_last_stages": ([C.POINTER(C.c_float), C.c_int, u64p], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():

@@ -139,9 +139,9 @@ struct alignas(16) G1Xyzz {
             j.x = Fq::zero(); j.y = Fq::one(); j.z = Fq::zero();
             return j;
         }
-        j.x = x * zz;
-        j.y = y * zzz;
-        j.z = zz;
+        j.x = (x * zz).canon();
+        j.y = (y * zzz).canon();
+        j.z = zz.canon();
         return j;
     }
 
@@ -155,8 +155,8 @@ struct alignas(16) G1Xyzz {
         // with zz = z^2, zzz = z^3:  1/zzz = z^-3 ;  1/zz = (z^-3)^2 * z^4 = zi^2 * zz^2
         Fq zi = zzz.inverse();
         Fq zzi = zi.sqr() * zz.sqr();
-        j.x = x * zzi;
-        j.y = y * zi;
+        j.x = (x * zzi).canon();
+        j.y = (y * zi).canon();
         j.z = Fq::one();
         return j;
     }

@@ -206,16 +206,33 @@ struct alignas(16) Fp {
         return r;
     }
 
-    ZK_HD bool is_zero() const {
-        return (l[0] | l[1] | l[2] | l[3] | l[4] | l[5] | l[6] | l[7]) == 0;
+    static ZK_HD void modulus2(uint32_t* m) {  // 2p
+        m[0] = P::P0 << 1;
+        m[1] = (P::P1 << 1) | (P::P0 >> 31); m[2] = (P::P2 << 1) | (P::P1 >> 31);
+        m[3] = (P::P3 << 1) | (P::P2 >> 31); m[4] = (P::P4 << 1) | (P::P3 >> 31);
+        m[5] = (P::P5 << 1) | (P::P4 >> 31); m[6] = (P::P6 << 1) | (P::P5 >> 31);
+        m[7] = (P::P7 << 1) | (P::P6 >> 31);
     }
-    ZK_HD bool operator==(const Fp& o) const {
+
+    // LAZY REDUCTION: every value of this type lives in [0, 2p) (p < 2^254, so 2p < 2^255
+    // and 4p < 2^256 = R).  Arithmetic keeps that invariant without ever reducing to
+    // [0, p); `canon()` produces the unique representative and is applied wherever a
+    // value leaves the library (stores to user-visible memory, digit extraction).
+    ZK_HD bool is_zero() const {   // value == 0 mod p, i.e. the limbs are 0 or p
+        const uint32_t z = l[0] | l[1] | l[2] | l[3] | l[4] | l[5] | l[6] | l[7];
+        const uint32_t e = (l[0] ^ P::P0) | (l[1] ^ P::P1) | (l[2] ^ P::P2) | (l[3] ^ P::P3) |
+                           (l[4] ^ P::P4) | (l[5] ^ P::P5) | (l[6] ^ P::P6) | (l[7] ^ P::P7);
+        return z == 0 || e == 0;
+    }
+    ZK_HD bool operator==(const Fp& o) const { return (*this - o).is_zero(); }
+    ZK_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+    // bit-for-bit comparison of representatives (host-side cache keys)
+    ZK_HD bool same_limbs(const Fp& o) const {
         uint32_t d = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) d |= l[i] ^ o.l[i];
         return d == 0;
     }
-    ZK_HD bool operator!=(const Fp& o) const { return !(*this == o); }
 
     // value in [0, 2p) -> [0, p)
     ZK_HD void reduce_once() {
@@ -225,36 +242,37 @@ struct alignas(16) Fp {
 #pragma unroll
         for (int i = 0; i < 8; ++i) l[i] = borrow ? l[i] : t[i];
     }
+    ZK_HD Fp canon() const {
+        Fp r = *this;
+        r.reduce_once();
+        return r;
+    }
 
     friend ZK_HD Fp operator+(const Fp& a, const Fp& b) {
         Fp r;
-        add8(r.l, a.l, b.l);  // a + b < 2p < 2^255: no carry
-        r.reduce_once();
+        uint32_t m[8], t[8];
+        modulus2(m);
+        add8(r.l, a.l, b.l);  // a + b < 4p < 2^256: no carry
+        uint32_t borrow = sub8(t, r.l, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = borrow ? r.l[i] : t[i];
         return r;
     }
     friend ZK_HD Fp operator-(const Fp& a, const Fp& b) {
         Fp r;
         uint32_t m[8], t[8];
-        modulus(m);
-        uint32_t borrow = sub8(r.l, a.l, b.l);
+        modulus2(m);
+        uint32_t borrow = sub8(r.l, a.l, b.l);   // in (-2p, 2p)
         add8(t, r.l, m);
 #pragma unroll
         for (int i = 0; i < 8; ++i) r.l[i] = borrow ? t[i] : r.l[i];
         return r;
     }
-    ZK_HD Fp neg() const {
-        Fp r;
-        uint32_t m[8];
-        modulus(m);
-        sub8(r.l, m, l);
-        bool z = is_zero();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r.l[i] = z ? 0u : r.l[i];
-        return r;
-    }
+    ZK_HD Fp neg() const { return zero() - *this; }
     ZK_HD Fp dbl() const { return *this + *this; }
 
-    // Montgomery product a*b*2^-256 mod p, inputs and output fully reduced.
+    // Montgomery product a*b*2^-256 mod p; inputs and output in [0, 2p): with 4p < R the
+    // result (a*b + M*p)/R < 4p^2/R + p < 2p needs no final subtraction.
     //
     // T = E + 2^32 * O (+ one stray limb carried between rows).  Row i adds a*b_i and
     // m*p with m chosen so the low limb cancels; V = T + a*b_i + m*p < 2^288, hence
@@ -291,24 +309,21 @@ struct alignas(16) Fp {
         }
         // merge: T = E + stray + 2^32 * O   (T < 2p < 2^255)
         Fp r;
-        uint32_t s[8], o[8];
+        uint32_t s[8];
         s[0] = stray;
 #pragma unroll
         for (int j = 1; j < 8; ++j) s[j] = O[j - 1];
-        add8(o, E, s);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r.l[j] = o[j];
-        r.reduce_once();
+        add8(r.l, E, s);
         return r;
     }
     ZK_HD Fp sqr() const { return (*this) * (*this); }
 
     // canonical integer -> Montgomery, and back
     ZK_HD Fp to_mont() const { return (*this) * r2(); }
-    ZK_HD Fp from_mont() const {
+    ZK_HD Fp from_mont() const {   // canonical integer (fully reduced)
         Fp o = zero();
         o.l[0] = 1;
-        return (*this) * o;
+        return ((*this) * o).canon();
     }
 
     // a^e for a 256-bit exponent given as 8 limbs (variable time)

@@ -509,6 +509,8 @@ struct MsmInfo { uint64_t n; uint32_t c, nwin, npairs, chunk; };
 static MsmInfo g_msm_info = {0, 0, 0, 0, 0};
 static bool g_msm_profile = false;
 static uint32_t g_msm_max_chunk = 128;   // tunable (b200zk_msm_tune)
+static uint32_t g_msm_max_seglen = 256;
+static uint32_t g_msm_force_c = 0;
 static cudaEvent_t g_msm_ev[MSM_ST_COUNT];
 static bool g_msm_ev_made = false, g_msm_ev_valid[MSM_ST_COUNT];
 static cudaStream_t g_msm_ev_stream = nullptr;
@@ -622,7 +624,7 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
         ZK_CUDA(cudaStreamSynchronize(s));
         return;
     }
-    const uint32_t cbits = pre ? pre->c : choose_window(n, false);
+    const uint32_t cbits = pre ? pre->c : (g_msm_force_c ? g_msm_force_c : choose_window(n, false));
     const uint32_t nwin = (255 + cbits - 1) / cbits;
     const uint32_t key_windows = pre ? 1u : nwin;
     const uint32_t nb = 1u << (cbits - 1);
@@ -638,7 +640,7 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     const uint32_t scan_blocks = (uint32_t)((nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK);
     // segment length of the bucket reduction: enough segments to fill the machine, short
     // enough that 2 * seglen dependent additions stay cheap
-    uint32_t seglen = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(4, nkeys / ((uint64_t)c.sm_count * 256)));
+    uint32_t seglen = (uint32_t)std::min<uint64_t>(g_msm_max_seglen, std::max<uint64_t>(4, nkeys / ((uint64_t)c.sm_count * 256)));
     if (seglen > nb) seglen = nb;
     const uint32_t segs_per_group = (nb + seglen - 1) / seglen;
     const size_t red_entries = (size_t)segs_per_group * groups;
@@ -900,10 +902,14 @@ int b200zk_msm_g1_dev_async(const void* d_scalars, const void* d_bases, size_t n
     });
 }
 
-int b200zk_msm_tune(uint32_t max_chunk) {
+int b200zk_msm_tune(uint32_t max_chunk, uint32_t max_seglen, uint32_t force_window_bits) {
     return guarded([&] {
         ZK_REQUIRE(max_chunk >= 4 && max_chunk <= 4096, "max_chunk out of range");
+        ZK_REQUIRE(max_seglen >= 4 && max_seglen <= 4096, "max_seglen out of range");
+        ZK_REQUIRE(force_window_bits == 0 || (force_window_bits >= 4 && force_window_bits <= 23), "window bits out of range");
         g_msm_max_chunk = max_chunk;
+        g_msm_max_seglen = max_seglen;
+        g_msm_force_c = force_window_bits;
     });
 }
 

@@ -24,7 +24,7 @@ static void plan_bits(uint32_t log_n, int& npass, int* bits) {
 
 NttTables* ntt_get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStream_t s) {
     for (NttTables* t : c.ntt_tables)
-        if (t->log_n == log_n && t->omega == omega) return t;
+        if (t->log_n == log_n && t->omega.same_limbs(omega)) return t;
     ZK_REQUIRE(log_n >= 1 && log_n <= 28, "log_n out of range (1..28)");
     NttTables* t = new NttTables();
     t->omega = omega;
@@ -173,7 +173,7 @@ static void ntt_run(Context& c, const Fr* in, uint64_t in_stride, Fr* out, uint6
 static __global__ void fr_scale_table_kernel(Fr* a, size_t n, const Fr* table, uint32_t mask) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr x = ldg_fr(a + i) * ldg_fr(table + (i & mask));
+    Fr x = (ldg_fr(a + i) * ldg_fr(table + (i & mask))).canon();
     st_fr(a + i, x);
 }
 

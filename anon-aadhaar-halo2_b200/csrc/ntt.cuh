@@ -275,6 +275,7 @@ __device__ __forceinline__ void ntt_round(const NttPassArgs& A, const Fr* __rest
                         const uint32_t r3 = oi % 3u;
                         x = x * (r3 == 0 ? A.out_tab[0] : (r3 == 1 ? A.out_tab[1] : A.out_tab[2]));
                     }
+                    if (A.last) x = x.canon();   // values leave the library fully reduced
                     if constexpr (FIRST) {
                         st_fr(stage + (colv[g] << B) + ip, x);
                     } else {

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) quotient_graph_kernel(const __grid_consta
         inter[c.target] = v;
         last = v;
     }
-    st_fr(G.out + idx, last);
+    st_fr(G.out + idx, last.canon());
 }
 
 struct PermDev {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) quotient_permutation_kernel(const __grid_
         }
         v = v * P.y + (left - right) * l_active;
     }
-    st_fr(P.values + idx, v);
+    st_fr(P.values + idx, v.canon());
 }
 
 struct LookupDev {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) quotient_lookup_kernel(const __grid_const
     }
     v = v * L.y + a_minus_s * l0;
     v = v * L.y + a_minus_s * (a - ldg_fr(L.permuted_input + r_prev)) * l_active;
-    st_fr(L.values + idx, v);
+    st_fr(L.values + idx, v.canon());
 }
 
 // ------------------------------------------------------------------------ host side

@@ -46,7 +46,8 @@ inline zk::Fr to_dev(const Fr& a) {
     for (int i = 0; i < 4; ++i) { r.l[2 * i] = (uint32_t)a[i]; r.l[2 * i + 1] = (uint32_t)(a[i] >> 32); }
     return r;
 }
-inline Fr from_dev(const zk::Fr& a) {
+inline Fr from_dev(const zk::Fr& lazy) {
+    const zk::Fr a = lazy.canon();   // field.cuh keeps values in [0, 2p); the wire type is reduced
     Fr r;
     for (int i = 0; i < 4; ++i) r[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
     return r;

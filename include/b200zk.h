@@ -204,8 +204,9 @@ int b200zk_modmul_peak(uint32_t iters, double* modmul_per_s_out);
  * durations {hist, scan, scatter, sync, accumulate, combine, reduce, reduce-combine, fold}
  * and info_out with {n, window bits c, windows, (bucket, point) pairs, chunk length}. */
 int b200zk_msm_profile(int enable);
-/* Tuning knob (benchmarks only): longest chunk of sorted pairs one thread accumulates. */
-int b200zk_msm_tune(uint32_t max_chunk);
+/* Tuning knobs (benchmarks only): longest chunk of sorted pairs one thread accumulates, longest
+ * bucket segment one thread reduces, and a forced window size (0 = cost model). */
+int b200zk_msm_tune(uint32_t max_chunk, uint32_t max_seglen, uint32_t force_window_bits);
 int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]);
 /* Number of kernels launched by this library since init (for bench.py gpu_launches). */
 uint64_t b200zk_kernel_launches(void);

@@ -10,7 +10,7 @@ names = ["hist", "scan", "scatter", "sync", "accum", "combine", "reduce", "red_c
 stream = torch.cuda.Stream(); st = C.c_void_p(stream.cuda_stream)
 b200zk.check(lib.b200zk_msm_profile(1))
 ks = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [15, 16, 18, 20, 22, 24]
-caps = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [32, 128]
+caps = [tuple(int(y) for y in x.split(":")) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [(128, 32, 0), (128, 128, 0)]
 for k in ks:
     n = 1 << k
     ds = torch.empty(n * 4, dtype=torch.int64, device="cuda"); db = torch.empty(n * 8, dtype=torch.int64, device="cuda")
@@ -18,7 +18,7 @@ for k in ks:
     b200zk.check(lib.b200zk_gen_points_dev(C.c_void_p(db.data_ptr()), n, 0xBA5E0000 + k, 0))
     out = np.zeros(12, dtype=np.uint64); ref = None
     for cap in caps:
-        b200zk.check(lib.b200zk_msm_tune(cap))
+        b200zk.check(lib.b200zk_msm_tune(*cap))
         with torch.cuda.stream(stream):
             def run(): b200zk.check(lib.b200zk_msm_g1_dev(C.c_void_p(ds.data_ptr()), C.c_void_p(db.data_ptr()), n, _ptr(out), st))
             run(); torch.cuda.synchronize()

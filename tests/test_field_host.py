@@ -40,6 +40,15 @@ def test_montgomery_field_ops(flib, p, pre):
             assert _call(flib, f"h_{pre}_add", a, b) == (a + b) % p
             assert _call(flib, f"h_{pre}_sub", a, b) == (a - b) % p
         assert _call(flib, f"h_{pre}_neg", a) == (-a) % p
+    # lazy representatives: inputs anywhere in [0, 2p), raw outputs stay in [0, 2p)
+    lazy = vals[:40] + [v + p for v in vals[:40]]
+    for a in lazy:
+        for b in rnd.sample(lazy, 6) + [p, p - 1 + p, 2 * p - 1, 0]:
+            for op, exp in (("mul", a * b * rinv), ("add", a + b), ("sub", a - b)):
+                raw = _call(flib, f"h_{pre}_{op}_raw", a, b)
+                assert raw < 2 * p and raw % p == exp % p, (op, hex(a), hex(b))
+                assert _call(flib, f"h_{pre}_{op}", a, b) == exp % p
+        assert bool(getattr(flib, f"h_{pre}_is_zero")((ctypes.c_uint32 * 8).from_buffer_copy(int(a).to_bytes(32, "little")))) == (a % p == 0)
     for a in vals[:24]:
         am = a * (1 << 256) % p
         if a:
