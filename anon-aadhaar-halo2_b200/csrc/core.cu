@@ -2,6 +2,7 @@
 // microbenchmark of the b200zk C ABI (include/b200zk.h).
 #include "../../include/b200zk.h"
 #include "common.cuh"
+#include <cstdlib>
 #include "ec.cuh"
 #include "ntt.cuh"
 

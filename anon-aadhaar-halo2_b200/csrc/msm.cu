@@ -28,6 +28,7 @@
 #include "ntt.cuh"  // ld_fr / st_fr helpers
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace zk {
@@ -227,20 +228,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __rest
 }
 
 // --------------------------------------------------------------------- 3. scatter
-// grid = (ceil(n / 256), columns * windows): blocks of one window are scheduled together.
+// grid = (ceil(n / 256), columns * windows * nsub): blocks of one (window, bucket sub-range)
+// are scheduled together; the digits are re-read nsub times, streaming.  The 4-byte stores
+// land at random places of the sorted list (ncu at k = 24: 9.8 GB of DRAM traffic for 1.6 GB
+// of algorithmic bytes: every store is a sector read-modify-write); restricting a pass to a
+// bucket sub-range narrows the set of lines being written.
 // The stored value is the index of the point to add: i, or w * table_stride + i into the
 // precomputed table, with the sign of the digit in bit 31.
 __global__ void msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n, uint32_t c, uint32_t nwin,
-                                   uint32_t key_windows, uint32_t table_stride, uint32_t* __restrict__ cursor,
-                                   uint32_t* __restrict__ sorted) {
+                                   uint32_t key_windows, uint32_t table_stride, uint32_t sub_bits,
+                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t cw = blockIdx.y;             // col * nwin + w
-    const int32_t d = __ldg(digits + (size_t)cw * n + i);
+    const uint32_t cw = blockIdx.y >> sub_bits;             // col * nwin + w
+    const uint32_t sub = blockIdx.y & ((1u << sub_bits) - 1u);
+    const int32_t d = __ldcs(digits + (size_t)cw * n + i);
     if (d == 0) return;
+    const uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+    if (((mag - 1) >> (c - 1 - sub_bits)) != sub) return;
     const uint32_t col = cw / nwin, w = cw - col * nwin;
     const uint32_t nb = 1u << (c - 1);
-    const uint32_t mag = (uint32_t)(d < 0 ? -d : d);
     const size_t group = (size_t)col * key_windows + (key_windows > 1 ? w : 0);
     const uint32_t pos = atomicAdd(cursor + group * nb + (mag - 1), 1u);
     sorted[pos] = ((uint32_t)i + w * table_stride) | (d < 0 ? 0x80000000u : 0u);
@@ -511,6 +518,8 @@ static bool g_msm_profile = false;
 static uint32_t g_msm_max_chunk = 128;   // tunable (b200zk_msm_tune)
 static uint32_t g_msm_max_seglen = 256;
 static uint32_t g_msm_force_c = 0;
+// scatter sub-range bits; B200ZK_MSM_SUB_BITS overrides the automatic choice (experiments only)
+static uint32_t g_msm_force_sub = getenv("B200ZK_MSM_SUB_BITS") ? (uint32_t)atoi(getenv("B200ZK_MSM_SUB_BITS")) : 0xffffffffu;
 static cudaEvent_t g_msm_ev[MSM_ST_COUNT];
 static bool g_msm_ev_made = false, g_msm_ev_valid[MSM_ST_COUNT];
 static cudaStream_t g_msm_ev_stream = nullptr;
@@ -684,8 +693,12 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, nkeys, total);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SCATTER);
-    msm_scatter_kernel<<<dim3(sblocks, (unsigned)(count * nwin)), 256, 0, s>>>(
-        digits, n, cbits, nwin, key_windows, pre ? (uint32_t)pre->n_reg : 0u, cursor, sorted);
+    // bucket sub-ranges: measured on B200 at k = 24, one split helps the shared-bucket (table)
+    // layout (6.4 -> 5.5 ms) and none helps the per-window layout
+    uint32_t sub_bits = (pre && n * 4 > ((size_t)16 << 20) && cbits > 2 && count * nwin * 2 <= 65535) ? 1u : 0u;
+    if (g_msm_force_sub != 0xffffffffu) sub_bits = std::min<uint32_t>(g_msm_force_sub, cbits - 1);
+    msm_scatter_kernel<<<dim3(sblocks, (unsigned)((count * nwin) << sub_bits)), 256, 0, s>>>(
+        digits, n, cbits, nwin, key_windows, pre ? (uint32_t)pre->n_reg : 0u, sub_bits, cursor, sorted);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SYNC);
     uint32_t npairs = 0;
