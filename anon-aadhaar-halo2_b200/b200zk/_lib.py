@@ -72,6 +72,7 @@ def load() -> C.CDLL:
         "b200zk_g1_sum": ([vp, sz, vp], C.c_int),
         "b200zk_dev_alloc": ([sz, u64p], C.c_int),
         "b200zk_dev_free": ([u64], C.c_int),
+        "b200zk_dev_view": ([u64, sz, sz, u64p], C.c_int),
         "b200zk_dev_upload": ([u64, sz, vp, sz], C.c_int),
         "b200zk_dev_download": ([u64, sz, vp, sz], C.c_int),
         "b200zk_dev_ptr": ([u64], vp),

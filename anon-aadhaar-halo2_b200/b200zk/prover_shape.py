@@ -1,0 +1,253 @@
+"""The hot-path call sequence of one `create_proof` at the shape of the reference's
+RSA-SHA256 circuit, on synthetic columns (SURVEY.md section 8 d, "Config 3 shape").
+
+The reference never runs the real prover and its circuits cannot be compiled
+here (F4), so the witness is replaced by seeded random columns of the same *shape*:
+k = 15 (reference src/lib.rs:444), constraint degree 4 => extended k = 17, about 112 advice
+columns, 24 lookups, 84 fixed columns, 115 permutation columns (58 grand products of chunk 2),
+3 quotient pieces.  What is timed is exactly the sequence of `ParamsKZG::commit_lagrange`,
+`lagrange_to_coeff`, `coeff_to_extended`, `evaluate_h`, `divide_by_vanishing_poly`,
+`extended_to_coeff` and `commit` calls `create_proof` makes ([DEP] halo2_proofs
+src/plonk/prover.rs @ v2023_01_20), batched per prover phase, all device-resident.  Witness
+synthesis, transcripts, grand-product construction and the SHPLONK opening are not part of
+the hot path and are not timed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import check, load
+from .api import EvaluationDomain, FR_ZETA, _ptr, fr_limbs
+from .quotient import FR_DELTA, DeviceColumn, EnvC, FlatGraph, _handles, _ptr32
+
+
+@dataclass
+class Shape:
+    k: int = 15
+    degree: int = 4                 # cs.degree(): extended k = k + 2, chunk = degree - 2 = 2
+    advice: int = 112
+    gate_columns: int = 80          # halo2-base FlexGate columns: q * (a0 + a1 * a2 - a3)
+    lookups: int = 24
+    fixed: int = 84
+    instance: int = 2
+    permutation_columns: int = 115
+    blinding_factors: int = 5
+
+    @property
+    def permutation_sets(self) -> int:
+        chunk = self.degree - 2
+        return -(-self.permutation_columns // chunk)
+
+    @property
+    def lagrange_columns(self) -> int:
+        """Columns committed in Lagrange basis and then taken to coefficient form."""
+        return self.advice + 3 * self.lookups + self.permutation_sets
+
+
+RSA_SHA256 = Shape()
+SMALL = Shape(k=8, advice=12, gate_columns=8, lookups=3, fixed=10, instance=1, permutation_columns=9)
+
+# b200zk_src kinds / b200zk_calc ops (include/b200zk.h)
+_CONST, _INTER, _FIXED, _ADVICE, _INSTANCE, _CHALL, _BETA, _GAMMA, _THETA, _Y, _PREV = range(11)
+_ADD, _SUB, _MUL, _SQUARE, _DOUBLE, _NEGATE, _HORNER, _STORE = range(8)
+
+
+def gate_graph(shape: Shape) -> FlatGraph:
+    """`GraphEvaluator` of the custom gates, flattened as upstream would produce it: one
+    FlexGate-style constraint q_c * (a_c + a_c[+1] * a_c[+2] - a_c[+3]) per gate column, each
+    sub-expression its own intermediate, then the y-Horner over all constraints."""
+    rotations = np.array([0, 1, 2, 3], dtype=np.int32)
+    calcs, parts = [], []
+    t = 0
+    for c in range(shape.gate_columns):
+        q = c % shape.fixed
+        calcs.append([_MUL, t, _ADVICE, c, 1, _ADVICE, c, 2, 0, 0])
+        calcs.append([_ADD, t + 1, _ADVICE, c, 0, _INTER, t, 0, 0, 0])
+        calcs.append([_SUB, t + 2, _INTER, t + 1, 0, _ADVICE, c, 3, 0, 0])
+        calcs.append([_MUL, t + 3, _FIXED, q, 0, _INTER, t + 2, 0, 0, 0])
+        parts.append([_INTER, t + 3, 0])
+        t += 4
+    calcs.append([_HORNER, t, _PREV, 0, 0, _Y, 0, 0, 0, len(parts)])
+    return FlatGraph(np.zeros((1, 4), np.uint64), rotations, np.array(calcs, np.uint32),
+                     np.array(parts, np.uint32), t + 1)
+
+
+def lookup_graph(shape: Shape, j: int) -> FlatGraph:
+    """(compressed_input + beta) * (compressed_table + gamma) for lookup j: a two-expression
+    input (theta-compressed) against a two-column table."""
+    a0 = shape.gate_columns + (j % max(1, shape.advice - shape.gate_columns))
+    a1 = (a0 + 1) % shape.advice
+    f0, f1 = (shape.fixed - 1 - j) % shape.fixed, (shape.fixed - 2 - j) % shape.fixed
+    calcs = [
+        [_HORNER, 0, _CONST, 0, 0, _THETA, 0, 0, 0, 2],      # ((0 * theta) + in0) * theta + in1
+        [_HORNER, 1, _CONST, 0, 0, _THETA, 0, 0, 2, 2],
+        [_ADD, 2, _INTER, 0, 0, _BETA, 0, 0, 0, 0],
+        [_ADD, 3, _INTER, 1, 0, _GAMMA, 0, 0, 0, 0],
+        [_MUL, 4, _INTER, 2, 0, _INTER, 3, 0, 0, 0],
+    ]
+    parts = [[_ADVICE, a0, 0], [_ADVICE, a1, 0], [_FIXED, f0, 0], [_FIXED, f1, 0]]
+    return FlatGraph(np.zeros((1, 4), np.uint64), np.array([0], np.int32), np.array(calcs, np.uint32),
+                     np.array(parts, np.uint32), 5)
+
+
+class ProverHotPath:
+    """Device-resident state of one proof's hot path + `run()`."""
+
+    def __init__(self, shape: Shape = RSA_SHA256, seed: int = 0x5EED0000, sync=None):
+        self.shape, self.lib = shape, load()
+        self.sync = sync or (lambda: None)
+        lib = self.lib
+        s = shape
+        self.domain = d = EvaluationDomain(s.degree, s.k)
+        self.n, self.N = d.n, d.extended_len()
+        n, N = self.n, self.N
+        # ---- ParamsKZG: synthetic SRS (g and g_lagrange share one table here)
+        pts = DeviceColumn(2 * n)                       # n points = 2n field elements
+        check(lib.b200zk_gen_points_dev(C.c_void_p(pts.ptr), n, seed, 0))
+        hp = pts.to_host().reshape(n, 8)
+        pts.free()
+        h = C.c_uint64(0)
+        check(lib.b200zk_bases_register(_ptr(hp), n, C.byref(h)))
+        self.h_bases = h.value
+        # ---- proving key: extended-domain fixed / sigma / l_0 / l_last / l_active columns
+        self.pk_cols = DeviceColumn((s.fixed + s.permutation_columns + 3) * N)
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.pk_cols.ptr), self.pk_cols.n, seed + 1, 0))
+        views = [DeviceColumn.view(self.pk_cols, i * N, N) for i in range(s.fixed + s.permutation_columns + 3)]
+        self.fixed = views[: s.fixed]
+        self.sigma = views[s.fixed: s.fixed + s.permutation_columns]
+        self.l0, self.l_last, self.l_active = views[-3:]
+        # ---- witness-shaped columns (Lagrange basis), one allocation per prover phase
+        self.n_lag = s.lagrange_columns
+        self.lag = DeviceColumn(self.n_lag * n)
+        self.instance_coeff = DeviceColumn(s.instance * n)
+        self.ext = DeviceColumn((self.n_lag + s.instance) * N)
+        self.ext_views = [DeviceColumn.view(self.ext, i * N, N) for i in range(self.n_lag + s.instance)]
+        self.values = DeviceColumn(N)
+        self.table = DeviceColumn(N)
+        self.h_coeff = DeviceColumn(n * (s.degree - 1))
+        self.points = DeviceColumn((self.n_lag + 1 + s.degree - 1) * 3)   # 12 limbs = 3 field elements each
+        self.seed = seed
+        self.gates = gate_graph(s)
+        self.lookup_graphs = [lookup_graph(s, j) for j in range(s.lookups)]
+        rnd = np.random.Generator(np.random.PCG64(seed))
+        self.scalars = {nm: fr_limbs(int.from_bytes(rnd.bytes(31), "little")) for nm in ("beta", "gamma", "theta", "y")}
+        perm_cols = [("advice", i % s.advice) for i in range(s.permutation_columns - s.instance)]
+        perm_cols += [("instance", i) for i in range(s.instance)]
+        self.perm_kind = np.array([{"fixed": 2, "advice": 3, "instance": 4}[k] for k, _ in perm_cols], np.uint32)
+        self.perm_index = np.array([i for _, i in perm_cols], np.uint32)
+
+    # column order inside `lag` / `ext`: advice | permuted input, permuted table (per lookup) |
+    # permutation products | lookup products
+    def _env(self):
+        s = self.shape
+        advice = self.ext_views[: s.advice]
+        instance = self.ext_views[self.n_lag: self.n_lag + s.instance]
+        keep = [_handles(self.fixed), _handles(advice), _handles(instance), np.zeros((1, 4), np.uint64)]
+        env = EnvC()
+        env.fixed, env.n_fixed = keep[0].ctypes.data, len(self.fixed)
+        env.advice, env.n_advice = keep[1].ctypes.data, len(advice)
+        env.instance, env.n_instance = keep[2].ctypes.data, len(instance)
+        env.challenges, env.n_challenges = keep[3].ctypes.data, 0
+        for name in ("beta", "gamma", "theta", "y"):
+            getattr(env, name)[:] = [int(x) for x in self.scalars[name]]
+        env.k, env.ext_k = self.domain.k, self.domain.extended_k
+        env.range_begin, env.range_len = 0, 0
+        env._keep = keep
+        return env
+
+    def _commit(self, ptr: int, count: int, out_index: int, length: int = None) -> None:
+        length = length or self.n
+        out = self.points.ptr + out_index * 96
+        check(self.lib.b200zk_msm_g1_registered_dev(self.h_bases, C.c_void_p(ptr), length, count, length,
+                                                    C.c_void_p(out), None))
+
+    def run(self) -> dict:
+        """One proof's hot path; returns wall-clock milliseconds per stage (device synchronised
+        at every stage boundary)."""
+        lib, s, d, n, N = self.lib, self.shape, self.domain, self.n, self.N
+        t = {}
+        marks = [time.perf_counter()]
+
+        def mark(name):
+            self.sync()
+            marks.append(time.perf_counter())
+            t[name] = 1e3 * (marks[-1] - marks[-2])
+
+        # fresh witness-shaped columns (not timed: stands in for synthesis)
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.lag.ptr), self.lag.n, self.seed + 2, 0))
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.instance_coeff.ptr), self.instance_coeff.n, self.seed + 3, 0))
+        self.sync()
+        marks[0] = time.perf_counter()
+        # ---- commitments in Lagrange basis, one batch per prover phase
+        col = 0
+        for count in (s.advice, 2 * s.lookups, s.permutation_sets + s.lookups):
+            self._commit(self.lag.ptr + col * n * 32, count, col)
+            col += count
+        mark("commit_lagrange")
+        # ---- lagrange_to_coeff, all columns
+        check(lib.b200zk_ntt_dev(C.c_void_p(self.lag.ptr), n, self.n_lag, d.k, _ptr(d.omega_inv),
+                                 _ptr(d.ifft_divisor), None))
+        mark("lagrange_to_coeff")
+        # ---- coeff_to_extended, all columns + instances
+        check(lib.b200zk_coeff_to_extended_dev(C.c_void_p(self.lag.ptr), n, C.c_void_p(self.ext.ptr), N, self.n_lag,
+                                               d.k, d.extended_k, _ptr(d.extended_omega), _ptr(d.g_coset), None))
+        check(lib.b200zk_coeff_to_extended_dev(C.c_void_p(self.instance_coeff.ptr), n,
+                                               C.c_void_p(self.ext.ptr + self.n_lag * N * 32), N, s.instance, d.k,
+                                               d.extended_k, _ptr(d.extended_omega), _ptr(d.g_coset), None))
+        mark("coeff_to_extended")
+        # ---- evaluate_h
+        env = self._env()
+        g = self.gates.as_c()
+        check(lib.b200zk_quotient_graph(C.byref(g), C.byref(env), 0, self.values.handle))
+        mark("quotient_gates")
+        lk0 = s.advice
+        pp0 = s.advice + 2 * s.lookups
+        lp0 = pp0 + s.permutation_sets
+        products = self.ext_views[pp0: pp0 + s.permutation_sets]
+        sig, ph = _handles(self.sigma), _handles(products)
+        zeta, delta = fr_limbs(FR_ZETA), fr_limbs(FR_DELTA)
+        check(lib.b200zk_quotient_permutation(
+            C.byref(env), self.values.handle, _ptr32(self.perm_kind), _ptr32(self.perm_index), _ptr(sig),
+            len(self.perm_kind), _ptr(ph), len(products), s.degree - 2, s.blinding_factors, self.l0.handle,
+            self.l_last.handle, self.l_active.handle, _ptr(d.extended_omega), _ptr(zeta), _ptr(delta)))
+        mark("quotient_permutation")
+        for j in range(s.lookups):
+            lg = self.lookup_graphs[j].as_c()
+            check(lib.b200zk_quotient_graph(C.byref(lg), C.byref(env), 0, self.table.handle))
+            check(lib.b200zk_quotient_lookup(C.byref(env), self.values.handle, self.table.handle,
+                                             self.ext_views[lp0 + j].handle, self.ext_views[lk0 + 2 * j].handle,
+                                             self.ext_views[lk0 + 2 * j + 1].handle, self.l0.handle,
+                                             self.l_last.handle, self.l_active.handle))
+        mark("quotient_lookups")
+        # ---- h(X) = numerator / (X^n - 1), back to coefficients, commit the pieces
+        t_ev = DeviceColumn.from_host(d.t_evaluations)
+        keep = n * (s.degree - 1)
+        check(lib.b200zk_extended_to_coeff_dev(C.c_void_p(self.values.ptr), d.extended_k, _ptr(d.extended_omega_inv),
+                                               _ptr(d.extended_ifft_divisor), _ptr(d.g_coset), C.c_void_p(t_ev.ptr),
+                                               d.t_evaluations.shape[0], C.c_void_p(self.h_coeff.ptr), keep, None))
+        mark("divide_and_extended_to_coeff")
+        self._commit(self.h_coeff.ptr, s.degree - 1, self.n_lag + 1)
+        mark("commit_h_pieces")
+        t_ev.free()
+        t["total"] = sum(t.values())
+        return t
+
+    def counts(self) -> dict:
+        s = self.shape
+        return {"commit_lagrange": s.lagrange_columns, "commit": s.degree - 1, "lagrange_to_coeff": s.lagrange_columns,
+                "coeff_to_extended": s.lagrange_columns + s.instance, "extended_to_coeff": 1,
+                "quotient_columns_read": s.fixed + s.advice + s.instance + 2 * s.permutation_columns +
+                                         s.permutation_sets + 3 * s.lookups + 3,
+                "k": s.k, "extended_k": self.domain.extended_k}
+
+    def close(self) -> None:
+        self.lib.b200zk_bases_evict(self.h_bases)
+        for v in self.ext_views + self.fixed + self.sigma + [self.l0, self.l_last, self.l_active]:
+            v.free()
+        for c in (self.pk_cols, self.lag, self.instance_coeff, self.ext, self.values, self.table, self.h_coeff,
+                  self.points):
+            c.free()

@@ -69,6 +69,16 @@ class DeviceColumn:
         check(col._lib.b200zk_dev_upload(col.handle, 0, _ptr(a), a.shape[0]))
         return col
 
+    @classmethod
+    def view(cls, parent: "DeviceColumn", offset: int, n_elems: int) -> "DeviceColumn":
+        """A second handle onto parent[offset : offset + n_elems] (no copy)."""
+        col = cls.__new__(cls)
+        col._lib = load()
+        h = C.c_uint64(0)
+        check(col._lib.b200zk_dev_view(parent.handle, offset, n_elems, C.byref(h)))
+        col.handle, col.n, col._parent = h.value, n_elems, parent
+        return col
+
     def to_host(self) -> np.ndarray:
         out = np.zeros((self.n, 4), dtype=np.uint64)
         check(self._lib.b200zk_dev_download(self.handle, 0, _ptr(out), self.n))

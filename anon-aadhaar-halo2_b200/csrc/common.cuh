@@ -86,6 +86,7 @@ struct BaseTable;
 struct DevBuffer {
     void* p = nullptr;
     size_t n_elems = 0;
+    bool owned = true;   // false: a view into another buffer (b200zk_dev_view)
 };
 
 struct Context {

@@ -158,7 +158,8 @@ int b200zk_shutdown(void) {
         msm_release_bases(c);
         for (Arena* a : {&c.ntt_io, &c.ntt_tmp, &c.ntt_aux, &c.msm_scalars, &c.msm_bases, &c.msm_work, &c.msm_carry, &c.misc, &c.quot_graph, &c.quot_ptrs})
             a->release();
-        for (auto& kv : c.buffers) cudaFree(kv.second.p);
+        for (auto& kv : c.buffers)
+            if (kv.second.owned) cudaFree(kv.second.p);
         c.buffers.clear();
         c.pinned.release();
         cudaStreamDestroy(c.stream);

@@ -276,8 +276,24 @@ int b200zk_dev_free(uint64_t handle) {
             cudaSetDevice(c.device);
             cudaStreamSynchronize(c.stream);
         }
-        cudaFree(it->second.p);
+        if (it->second.owned) cudaFree(it->second.p);
         c.buffers.erase(it);
+    });
+}
+
+int b200zk_dev_view(uint64_t parent, size_t offset, size_t n_elems, uint64_t* handle_out) {
+    return guarded([&] {
+        ZK_REQUIRE(handle_out, "null argument");
+        ensure_init();
+        Context& c = ctx();
+        DevBuffer& b = buffer_of(c, parent, offset + n_elems, "view");
+        DevBuffer v;
+        v.p = (Fr*)b.p + offset;
+        v.n_elems = n_elems;
+        v.owned = false;
+        const uint64_t h = c.next_handle++;
+        c.buffers[h] = v;
+        *handle_out = h;
     });
 }
 

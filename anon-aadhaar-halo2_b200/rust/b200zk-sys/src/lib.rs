@@ -61,6 +61,7 @@ extern "C" {
 
     pub fn b200zk_dev_alloc(n_elems: usize, handle_out: *mut u64) -> c_int;
     pub fn b200zk_dev_free(handle: u64) -> c_int;
+    pub fn b200zk_dev_view(parent: u64, offset: usize, n_elems: usize, handle_out: *mut u64) -> c_int;
     pub fn b200zk_dev_upload(handle: u64, offset: usize, host: *const u64, n_elems: usize) -> c_int;
     pub fn b200zk_dev_download(handle: u64, offset: usize, host: *mut u64, n_elems: usize) -> c_int;
     pub fn b200zk_dev_ptr(handle: u64) -> *mut c_void;

@@ -200,6 +200,8 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="print the k=16..26 table instead of the driver line")
+    ap.add_argument("--no-proof-shape", action="store_true",
+                    help="skip the RSA-SHA256-shaped create_proof hot-path pass (BASELINE.json configs[2] stand-in)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -419,6 +421,11 @@ def main() -> None:
                                   f"C restatement of the rayon CPU path, {threads} threads",
                         "msm_mpts_per_s": (1 << ck) / msm_s / 1e6, "ntt_melem_per_s": (1 << ck) / fft_s / 1e6}
 
+    # ---- configs[2] stand-in: one create_proof hot path at the RSA-SHA256 circuit shape
+    proof_shape = None
+    if not args.no_proof_shape:
+        proof_shape = run_proof_shape(torch, dist, world, rank, dev, cpu=(rank == 0 and world == 1 and not args.no_cpu))
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -431,11 +438,58 @@ def main() -> None:
             "ntt": {"ms": ntt_ms, "alg_GBps": ntt_gbs, "melem_per_s": n / (ntt_ms * 1e-3) / 1e6},
             "msm_unregistered": {"ms": unreg_ms, "mpts_per_s": n / (unreg_ms * 1e-3) / 1e6,
                                  "api": "b200zk_msm_g1_dev_async (best_multiexp, bases passed per call)"},
-            "srs_registration_s": t_reg,
+            "srs_registration_s": t_reg, "proof_shape": proof_shape,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_proof_shape(torch, dist, world: int, rank: int, dev, cpu: bool):
+    """The hot-path call sequence of one create_proof at the RSA-SHA256 circuit shape
+    (k = 15, extended k = 17; SURVEY.md section 8 d) on synthetic columns, every rank one
+    replica.  Returns per-stage milliseconds (median of 3 after one warm-up)."""
+    from b200zk.prover_shape import RSA_SHA256, ProverHotPath
+    hp = ProverHotPath(RSA_SHA256, sync=torch.cuda.synchronize)
+    hp.run()
+    runs = [hp.run() for _ in range(3)]
+    med = {k: statistics.median(r[k] for r in runs) for k in runs[0]}
+    tt = torch.tensor([med["total"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    out = {"workload": "synthetic stand-in for BASELINE.json configs[2] (RSA-SHA256 sub-circuit proof): the commit / "
+                       "iNTT / coset-NTT / evaluate_h / extended_to_coeff calls of one create_proof on seeded random "
+                       "columns of the circuit's shape; witness synthesis, transcript and SHPLONK opening excluded",
+           "calls": hp.counts(), "stages_ms": med, "hot_path_ms": float(tt.item()),
+           "proofs_per_s_all_gpus": world / (float(tt.item()) * 1e-3), "parallelism": "replicas only"}
+    hp.close()
+    if cpu:
+        from oracle import c_oracle as co
+        co.build()
+        threads = co.host_threads()
+        s = RSA_SHA256
+        n = 1 << s.k
+        sc = co.gen_scalars(SEED_S + s.k, n)
+        pts = co.gen_points(SEED_P + s.k, n, threads=threads)
+        sc_ext = co.gen_scalars(SEED_S + s.k + 2, 4 * n)
+        t0 = time.perf_counter()
+        for _ in range(4):
+            co.best_multiexp(sc, pts, threads)
+        t1 = time.perf_counter()
+        for _ in range(4):
+            co.best_fft(sc, fr_limbs(omega_for(s.k)), s.k, threads)
+        t2 = time.perf_counter()
+        for _ in range(4):
+            co.best_fft(sc_ext, fr_limbs(omega_for(s.k + 2)), s.k + 2, threads)
+        t3 = time.perf_counter()
+        c = out["calls"]
+        est = ((c["commit_lagrange"] + c["commit"]) * (t1 - t0) / 4 + c["lagrange_to_coeff"] * (t2 - t1) / 4 +
+               (c["coeff_to_extended"] + c["extended_to_coeff"]) * (t3 - t2) / 4)
+        out["cpu_baseline"] = {"value": 1e3 * est, "unit": "ms", "cores": threads, "kind": "port",
+                               "sample": "4 best_multiexp at 2^15, 4 best_fft at 2^15 and 4 at 2^17 timed on the C "
+                                         "restatement and scaled by the call counts; evaluate_h not included "
+                                         "(the estimate is a lower bound of the CPU hot path)"}
+    return out
 
 
 def sweep(args, torch, b200zk, lib, dev) -> None:

@@ -127,6 +127,11 @@ int b200zk_g1_sum(const uint64_t* points_xyz, size_t count, uint64_t out_xyz[12]
  * addressed by handle.  Sizes and offsets are in field elements (32 bytes). */
 int b200zk_dev_alloc(size_t n_elems, uint64_t* handle_out);
 int b200zk_dev_free(uint64_t handle);
+/* A second handle onto elements [offset, offset + n_elems) of `parent` (no copy; freeing the
+ * view leaves the parent alone, the parent must outlive it).  Lets a batch of columns live in
+ * one allocation for the strided `*_dev` transforms while the quotient kernels address them
+ * one by one. */
+int b200zk_dev_view(uint64_t parent, size_t offset, size_t n_elems, uint64_t* handle_out);
 int b200zk_dev_upload(uint64_t handle, size_t offset, const uint64_t* host, size_t n_elems);
 int b200zk_dev_download(uint64_t handle, size_t offset, uint64_t* host, size_t n_elems);
 /* Raw device pointer of a handle (NULL if unknown), for the *_dev entry points above. */
