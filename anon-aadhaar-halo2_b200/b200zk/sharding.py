@@ -84,3 +84,155 @@ def gather_extended_chunks(local_chunk: np.ndarray, size: int, device=None) -> n
         b, e = shard_range(size, r, world)
         out[b:e] = allc[r, : e - b]
     return out
+
+
+# ----------------------------------------------------------------- one NTT over several GPUs
+# SURVEY.md section 8 e, "single large NTT": the four-step split n = n1 * n2 with ONE exchange.
+# Input index j = j1 * n2 + j2, output index i = i1 + n1 * i2:
+#   A[i1 + n1 i2] = sum_j2 w^(n1 i2 j2) * w^(i1 j2) * ( sum_j1 a[j1 n2 + j2] * w^(n2 i1 j1) )
+# Rank r owns columns j2 in [r m, (r+1) m) (m = n2 / world) on the way in and rows
+# i1 in [r n1/world, (r+1) n1/world) on the way out; neither is a contiguous slice of the
+# natural order, which is what makes one all-to-all enough (the host-side scatter / gather of
+# a natural-order vector is a strided copy, `column_block` / `natural_from_row_blocks`).
+
+def four_step_split(k: int, world: int) -> int:
+    """log2(n1) for a 2^k transform over `world` ranks (both factors >= world)."""
+    lw = world.bit_length() - 1
+    assert world == 1 << lw, "world size must be a power of two"
+    log_n1 = (k + 1) // 2
+    assert log_n1 >= lw and k - log_n1 >= lw, "transform too small for this many ranks"
+    return log_n1
+
+
+def column_block(a: np.ndarray, k: int, log_n1: int, world: int, rank: int) -> np.ndarray:
+    """Rank's input share of a natural-order vector a (n, 4): X[j2 - r m][j1] = a[j1 n2 + j2]."""
+    n1, n2 = 1 << log_n1, 1 << (k - log_n1)
+    m = n2 // world
+    mat = a.reshape(n1, n2, 4)
+    return np.ascontiguousarray(mat[:, rank * m:(rank + 1) * m].transpose(1, 0, 2))
+
+
+def natural_from_row_blocks(blocks, k: int, log_n1: int) -> np.ndarray:
+    """Inverse of the output distribution: blocks[s][il][i2] = A[(s n1/world + il) + n1 i2]."""
+    n1, n2 = 1 << log_n1, 1 << (k - log_n1)
+    rows = np.concatenate(list(blocks), axis=0)            # [i1][i2]
+    assert rows.shape[:2] == (n1, n2)
+    return np.ascontiguousarray(rows.transpose(1, 0, 2)).reshape(n1 * n2, 4)
+
+
+def sharded_best_fft(x_local, k: int, omega: int, ops, world: int, rank: int):
+    """`best_fft` of 2^k elements over `world` ranks.  `x_local` is this rank's column block
+    ([m][n1], see column_block); the result is its row block ([n1 / world][n2]).  `ops`
+    supplies the local steps and the exchange (DeviceFourStep below on GPUs; the CPU tests
+    inject the oracle):
+        ops.ntt_rows(buf, count, log_len, omega)     in-place transforms of contiguous rows
+        ops.twiddle_exchange(buf, k, log_n1, omega)  -> this rank's [n1 / world][n2] row block
+    """
+    from .api import FR_MODULUS
+    log_n1 = four_step_split(k, world)
+    log_n2 = k - log_n1
+    n1, n2 = 1 << log_n1, 1 << log_n2
+    ops.ntt_rows(x_local, n2 // world, log_n1, pow(omega, n2, FR_MODULUS))
+    rows = ops.twiddle_exchange(x_local, k, log_n1, omega)
+    ops.ntt_rows(rows, n1 // world, log_n2, pow(omega, n1, FR_MODULUS))
+    return rows
+
+
+class DeviceFourStep:
+    """Device implementation of the two local steps and the exchange.  Buffers are torch
+    int64 CUDA tensors (4 limbs per element).  Exchange modes:
+      * "p2p"  : the twiddle kernel stores straight into the peers' row buffers through
+                 symmetric-memory mappings (NVLink / NVSwitch); no separate collective;
+      * "nccl" : the twiddle kernel packs per-destination chunks, `all_to_all_single`
+                 moves them, a strided copy lays the rows out."""
+
+    def __init__(self, k: int, world: int, rank: int, device, mode: str = "auto"):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from ._lib import check, load
+        self.C, self.torch, self.dist, self.check, self.lib = C, torch, dist, check, load()
+        self.k, self.world, self.rank, self.device = k, world, rank, device
+        self.log_n1 = four_step_split(k, world)
+        n1, n2 = 1 << self.log_n1, 1 << (k - self.log_n1)
+        self.rows_elems = (n1 // world) * n2
+        # a stream of our own: handle 0 (torch's default stream) would mean "the library's
+        # stream" to the C ABI, and the NCCL exchange must be ordered with the kernels
+        self.stream = torch.cuda.Stream(device=device)
+        self.mode = "nccl"
+        self.rows = None
+        if world > 1 and mode in ("auto", "p2p"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                self.rows = symm.empty(self.rows_elems * 4, dtype=torch.int64, device=device)
+                self.hdl = symm.rendezvous(self.rows, dist.group.WORLD.group_name)
+                self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+                self.mode = "p2p"
+            except Exception as e:   # no peer mapping available: fall back to the NCCL exchange
+                if mode == "p2p":
+                    raise
+                self.rows, self.p2p_error = None, repr(e)
+        if self.rows is None:
+            self.rows = torch.empty(self.rows_elems * 4, dtype=torch.int64, device=device)
+        if self.mode == "nccl":
+            self.send = torch.empty(self.rows_elems * 4, dtype=torch.int64, device=device)
+            self.recv = torch.empty(self.rows_elems * 4, dtype=torch.int64, device=device) if world > 1 else None
+
+    def _stream(self):
+        return self.C.c_void_p(self.stream.cuda_stream)
+
+    class _Ordered:
+        """Run a block on self.stream, ordered after and before the caller's current stream."""
+
+        def __init__(self, outer):
+            self.o = outer
+
+        def __enter__(self):
+            t = self.o.torch
+            self.cur = t.cuda.current_stream(self.o.device)
+            self.o.stream.wait_stream(self.cur)
+            self.ctx = t.cuda.stream(self.o.stream)
+            self.ctx.__enter__()
+
+        def __exit__(self, *exc):
+            self.ctx.__exit__(*exc)
+            self.cur.wait_stream(self.o.stream)
+            return False
+
+    def ntt_rows(self, buf, count: int, log_len: int, omega: int) -> None:
+        from .api import _ptr, fr_limbs
+        w = fr_limbs(omega)
+        with self._Ordered(self):
+            self.check(self.lib.b200zk_ntt_dev(self.C.c_void_p(buf.data_ptr()), 1 << log_len, count, log_len, _ptr(w),
+                                               None, self._stream()))
+
+    def twiddle_exchange(self, buf, k: int, log_n1: int, omega: int):
+        with self._Ordered(self):
+            return self._twiddle_exchange(buf, k, log_n1, omega)
+
+    def _twiddle_exchange(self, buf, k: int, log_n1: int, omega: int):
+        from .api import _ptr, fr_limbs
+        C, world, rank = self.C, self.world, self.rank
+        n1, n2 = 1 << log_n1, 1 << (k - log_n1)
+        m, rows = n2 // world, n1 // world
+        w = fr_limbs(omega)
+        bases = (C.c_void_p * world)()
+        if self.mode == "p2p":
+            self.hdl.barrier(channel=0)          # every peer is done reading its previous rows
+            for s in range(world):
+                bases[s] = self.peer_ptrs[s]
+            self.check(self.lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(buf.data_ptr()), k, log_n1, _ptr(w), world,
+                                                                rank, bases, n2, rank * m, self._stream()))
+            self.hdl.barrier(channel=1)          # every peer's stores into my rows have landed
+            return self.rows
+        dst = self.send if world > 1 else self.rows
+        for s in range(world):
+            bases[s] = dst.data_ptr() + s * rows * m * 32
+        self.check(self.lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(buf.data_ptr()), k, log_n1, _ptr(w), world, rank,
+                                                            bases, m, 0, self._stream()))
+        if world == 1:
+            return self.rows
+        self.dist.all_to_all_single(self.recv, self.send)
+        self.check(self.lib.b200zk_ntt4_gather_rows_dev(C.c_void_p(self.recv.data_ptr()), C.c_void_p(self.rows.data_ptr()),
+                                                        k, log_n1, world, self._stream()))
+        return self.rows

@@ -230,6 +230,65 @@ static NttMods coset_out_mods(const uint64_t* divisor, const uint64_t* zeta, siz
     return m;
 }
 
+
+// ---------------------------------------------------------------- multi-GPU four-step
+// One 2^log_n transform sharded over `world` GPUs (SURVEY.md section 8 e).  With
+// n = n1 * n2, input index j = j1 * n2 + j2 and output index i = i1 + n1 * i2:
+//   A[i1 + n1 i2] = sum_j2 w^(n1 i2 j2) * w^(i1 j2) * ( sum_j1 a[j1 n2 + j2] * w^(n2 i1 j1) ).
+// Rank r owns the columns j2 in [r m, (r+1) m), m = n2 / world, stored [m][n1]; it runs m
+// transforms of length n1 (b200zk_ntt_dev), then this kernel multiplies by w^(i1 j2) and
+// sends element (i1, j2) to the rank that owns row i1, into its [n1 / world][n2] buffer at
+// [i1 mod (n1 / world)][j2].  `dest[s]` is the base of rank s's buffer: either a peer
+// mapping (stores travel over NVLink, so the twiddle pass *is* the all-to-all) or a slice
+// of a local send buffer for a NCCL all-to-all.  A 32 x 32 tile is transposed through
+// shared memory so that both the loads (i1 fastest) and the stores (j2 fastest, 1 KiB
+// contiguous per row) are coalesced.
+struct Ntt4Args {
+    const Fr* in;
+    Fr* dest[8];
+    uint64_t dest_pitch, dest_col_offset;
+    const Fr* tw_lo;
+    const Fr* tw_hi;
+    uint32_t tw_h;
+    uint32_t log_n1, log_m, log_rows;   // rows per destination = n1 / world
+    uint32_t col0;                      // r * m
+};
+
+static __global__ void __launch_bounds__(256) ntt4_twiddle_scatter_kernel(const __grid_constant__ Ntt4Args A) {
+    __shared__ uint4 tile[2][32][33];
+    const uint32_t n1 = 1u << A.log_n1, m = 1u << A.log_m;
+    const uint32_t i1_0 = blockIdx.x * 32u, jl_0 = blockIdx.y * 32u;
+    const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (uint32_t rr = 0; rr < 32; rr += 8) {
+        const uint32_t jl = jl_0 + ty + rr, i1 = i1_0 + tx;
+        if (jl < m && i1 < n1) {
+            Fr x = ldg_fr(A.in + (size_t)jl * n1 + i1);
+            const uint32_t e = i1 * (A.col0 + jl);          // < n <= 2^28
+            if (e != 0) {
+                Fr t = ldg_fr(A.tw_lo + (e & ((1u << A.tw_h) - 1u)));
+                const uint32_t eh = e >> A.tw_h;
+                if (eh != 0) t = t * ldg_fr(A.tw_hi + eh);
+                x = x * t;
+            }
+            x = x.canon();
+            tile[0][ty + rr][tx] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
+            tile[1][ty + rr][tx] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t rr = 0; rr < 32; rr += 8) {
+        const uint32_t i1 = i1_0 + ty + rr, jl = jl_0 + tx;
+        if (jl < m && i1 < n1) {
+            const uint32_t s = i1 >> A.log_rows, il = i1 & ((1u << A.log_rows) - 1u);
+            uint4* q = reinterpret_cast<uint4*>(A.dest[s] + (size_t)il * A.dest_pitch + A.dest_col_offset + jl);
+            q[0] = tile[0][tx][ty + rr];
+            q[1] = tile[1][tx][ty + rr];
+        }
+    }
+}
+
 }  // namespace zk
 
 using namespace zk;
@@ -394,6 +453,59 @@ int b200zk_extended_to_coeff_dev(const void* d_a, uint32_t ext_k, const uint64_t
         Fr* tmp = (Fr*)c.ntt_tmp.get(N * sizeof(Fr));
         ntt_run(c, (const Fr*)d_a, N, io, N, tmp, 1, ext_k, fr_from_limbs(extended_omega_inv), m, s);
         ZK_CUDA(cudaMemcpyAsync(d_out, io, keep * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+    });
+}
+
+int b200zk_ntt4_twiddle_scatter_dev(const void* d_in, uint32_t log_n, uint32_t log_n1, const uint64_t omega[4],
+                                    uint32_t world, uint32_t rank, void* const* dest_bases, size_t dest_pitch,
+                                    size_t dest_col_offset, void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_in && omega && dest_bases, "null argument");
+        ZK_REQUIRE(world >= 1 && world <= 8 && (world & (world - 1)) == 0 && rank < world, "world must be 1, 2, 4 or 8");
+        ZK_REQUIRE(log_n >= 2 && log_n <= 28 && log_n1 >= 1 && log_n1 < log_n, "bad transform split");
+        uint32_t log_w = 0;
+        while ((1u << log_w) < world) ++log_w;
+        const uint32_t log_n2 = log_n - log_n1;
+        ZK_REQUIRE(log_n1 >= log_w && log_n2 >= log_w, "both factors must be at least the world size");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        NttTables* t = ntt_get_tables(c, fr_from_limbs(omega), log_n, s);
+        Ntt4Args a;
+        memset(&a, 0, sizeof a);
+        a.in = (const Fr*)d_in;
+        for (uint32_t i = 0; i < world; ++i) {
+            ZK_REQUIRE(dest_bases[i], "null destination buffer");
+            a.dest[i] = (Fr*)dest_bases[i];
+        }
+        a.dest_pitch = dest_pitch;
+        a.dest_col_offset = dest_col_offset;
+        a.tw_lo = t->tw_lo; a.tw_hi = t->tw_hi; a.tw_h = t->tw_h;
+        a.log_n1 = log_n1;
+        a.log_m = log_n2 - log_w;
+        a.log_rows = log_n1 - log_w;
+        a.col0 = rank << a.log_m;
+        const uint32_t n1 = 1u << log_n1, m = 1u << a.log_m;
+        ntt4_twiddle_scatter_kernel<<<dim3((n1 + 31) / 32, (m + 31) / 32), 256, 0, s>>>(a);
+        ZK_LAUNCH_CHECK();
+    });
+}
+
+int b200zk_ntt4_gather_rows_dev(const void* d_recv, void* d_out, uint32_t log_n, uint32_t log_n1, uint32_t world,
+                                void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_recv && d_out && d_recv != d_out, "bad buffers");
+        ZK_REQUIRE(world >= 1 && (world & (world - 1)) == 0, "world must be a power of two");
+        uint32_t log_w = 0;
+        while ((1u << log_w) < world) ++log_w;
+        ZK_REQUIRE(log_n1 < log_n && log_n1 >= log_w && log_n - log_n1 >= log_w, "bad transform split");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        const size_t rows = (size_t)1 << (log_n1 - log_w), n2 = (size_t)1 << (log_n - log_n1), m = n2 / world;
+        for (uint32_t r = 0; r < world; ++r)
+            ZK_CUDA(cudaMemcpy2DAsync((Fr*)d_out + r * m, n2 * sizeof(Fr), (const Fr*)d_recv + r * rows * m,
+                                      m * sizeof(Fr), m * sizeof(Fr), rows, cudaMemcpyDeviceToDevice, s));
     });
 }
 

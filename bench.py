@@ -421,6 +421,11 @@ def main() -> None:
                                   f"C restatement of the rayon CPU path, {threads} threads",
                         "msm_mpts_per_s": (1 << ck) / msm_s / 1e6, "ntt_melem_per_s": (1 << ck) / fft_s / 1e6}
 
+    # ---- N > 1: ONE best_fft of 2^k sharded over all ranks (four-step, one exchange over NVLink)
+    ntt_sharded = None
+    if world > 1:
+        ntt_sharded = run_sharded_ntt(torch, dist, lib, b200zk, world, rank, dev, k, ntt_ms)
+
     # ---- configs[2] stand-in: one create_proof hot path at the RSA-SHA256 circuit shape
     proof_shape = None
     if not args.no_proof_shape:
@@ -438,11 +443,44 @@ def main() -> None:
             "ntt": {"ms": ntt_ms, "alg_GBps": ntt_gbs, "melem_per_s": n / (ntt_ms * 1e-3) / 1e6},
             "msm_unregistered": {"ms": unreg_ms, "mpts_per_s": n / (unreg_ms * 1e-3) / 1e6,
                                  "api": "b200zk_msm_g1_dev_async (best_multiexp, bases passed per call)"},
-            "srs_registration_s": t_reg, "proof_shape": proof_shape,
+            "srs_registration_s": t_reg, "proof_shape": proof_shape, "ntt_sharded": ntt_sharded,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sharded_ntt(torch, dist, lib, b200zk, world: int, rank: int, dev, k: int, single_ms: float):
+    """One 2^k best_fft over all ranks (strong scaling of a single transform): local column
+    NTTs, twiddle pass that stores straight into the peers' row buffers over NVLink (falls back
+    to a NCCL all-to-all when peer mappings are unavailable), local row NTTs."""
+    from b200zk import sharding
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    n = 1 << k
+    log_n1 = sharding.four_step_split(k, world)
+    n1, n2 = 1 << log_n1, 1 << (k - log_n1)
+    m = n2 // world
+    x0 = torch.empty(m * n1 * 4, dtype=torch.int64, device=dev)
+    b200zk.check(lib.b200zk_gen_scalars_dev(vp(x0), m * n1, SEED_S + k, rank * m * n1))
+    ops = sharding.DeviceFourStep(k, world, rank, dev, mode="auto")
+    omega = omega_for(k)
+    reps = 5
+    xs = [x0.clone() for _ in range(reps + 1)]
+    sharding.sharded_best_fft(xs[reps], k, omega, ops, world, rank)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        sharding.sharded_best_fft(xs[i], k, omega, ops, world, rank)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"k": k, "ms": ms, "melem_per_s": n / ms / 1e3, "exchange": ops.mode,
+            "speedup_vs_one_gpu": single_ms / ms, "exchange_bytes_per_rank": (world - 1) * n * 32 // (world * world),
+            "layout": "rank r holds columns j2 in [r m, (r+1) m) in, rows i1 in [r n1/N, (r+1) n1/N) out"}
 
 
 def run_proof_shape(torch, dist, world: int, rank: int, dev, cpu: bool):

@@ -85,6 +85,26 @@ int b200zk_extended_to_coeff_dev(const void* d_a, uint32_t ext_k, const uint64_t
                                  const void* d_t_evaluations_or_null, uint32_t t_len, void* d_out, size_t keep,
                                  void* stream);
 
+/* One best_fft of 2^log_n elements sharded over `world` (1, 2, 4 or 8) GPUs, one process per
+ * GPU (SURVEY.md section 8 e).  n = n1 * n2 with n1 = 2^log_n1; rank r holds the columns
+ * j2 in [r m, (r + 1) m), m = n2 / world, as d_in[j2 - r m][j1] = a[j1 * n2 + j2].  The caller
+ *   1. runs b200zk_ntt_dev(d_in, n1, m, log_n1, omega^n2)                 (m transforms of n1),
+ *   2. calls b200zk_ntt4_twiddle_scatter_dev: multiply by omega^(i1 * j2) and store element
+ *      (i1, j2) at dest_bases[i1 / (n1 / world)] + (i1 mod (n1 / world)) * dest_pitch +
+ *      dest_col_offset + (j2 - r m)   [offsets in field elements].  With peer-mapped buffers
+ *      (dest_pitch = n2, dest_col_offset = r m) this pass is itself the all-to-all; with a
+ *      local send buffer (dest_bases[s] = send + s * (n1 / world) * m, dest_pitch = m, offset 0)
+ *      it packs for a NCCL all-to-all, whose result b200zk_ntt4_gather_rows_dev turns into
+ *      the [n1 / world][n2] row block,
+ *   3. runs b200zk_ntt_dev(rows, n2, n1 / world, log_n2, omega^n1): row i1 then holds
+ *      A[i1 + n1 * i2] at position i2.
+ * `dest_bases` is a host array of `world` device pointers. */
+int b200zk_ntt4_twiddle_scatter_dev(const void* d_in, uint32_t log_n, uint32_t log_n1, const uint64_t omega[4],
+                                    uint32_t world, uint32_t rank, void* const* dest_bases, size_t dest_pitch,
+                                    size_t dest_col_offset, void* stream);
+int b200zk_ntt4_gather_rows_dev(const void* d_recv, void* d_out, uint32_t log_n, uint32_t log_n1, uint32_t world,
+                                void* stream);
+
 /* ---- MSM: arithmetic::best_multiexp and ParamsKZG::commit / commit_lagrange -------- */
 /* halo2_proofs/src/arithmetic.rs `best_multiexp::<G1Affine>(coeffs, bases) -> G1`.
  * scalars: n x 4 limbs (Fr Montgomery); bases: n x 8 limbs (G1Affine); out: 12 limbs (G1). */

@@ -1,0 +1,97 @@
+"""The four-step sharded NTT (b200zk_ntt4_* + sharding.sharded_best_fft) on one GPU: every
+rank's steps are run one after the other in this process, with the twiddle kernel storing into
+the other "ranks'" row buffers exactly as it does into peer-mapped memory over NVLink.  The
+result must equal the oracle's best_fft bit for bit.  (Two real ranks over gloo: see
+tests/test_sharding_cpu.py; two real GPUs: scratch/gpu_ntt4.py under torchrun.)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as bn
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+
+class _OneGpuRanks:
+    """`ops` for sharded_best_fft that plays rank `rank` of `world` on the local GPU."""
+
+    def __init__(self, zk, k, world, rank, row_buffers):
+        self.zk, self.lib, self.k, self.world, self.rank, self.rows = zk, zk.load(), k, world, rank, row_buffers
+
+    def ntt_rows(self, col, count, log_len, omega):
+        from b200zk.api import _ptr, fr_limbs
+        w = fr_limbs(omega)
+        self.zk.check(self.lib.b200zk_ntt_dev(C.c_void_p(col.ptr), 1 << log_len, count, log_len, _ptr(w), None, None))
+
+    def twiddle_exchange(self, col, k, log_n1, omega):
+        from b200zk.api import _ptr, fr_limbs
+        n2 = 1 << (k - log_n1)
+        m = n2 // self.world
+        bases = (C.c_void_p * self.world)(*[r.ptr for r in self.rows])
+        w = fr_limbs(omega)
+        self.zk.check(self.lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(col.ptr), k, log_n1, _ptr(w), self.world,
+                                                               self.rank, bases, n2, self.rank * m, None))
+        return None
+
+
+@pytest.mark.parametrize("k,world", [(4, 1), (6, 2), (9, 2), (10, 4), (13, 8), (16, 4)])
+def test_four_step_matches_best_fft(zk, k, world):
+    from b200zk import sharding
+    from b200zk.api import FR_MODULUS, FR_ROOT_OF_UNITY
+    n = 1 << k
+    a = co.gen_scalars(0x4E54 + k, n)
+    omega = pow(FR_ROOT_OF_UNITY, 1 << (28 - k), FR_MODULUS)
+    want = co.best_fft(a.copy(), bn.fr_array_from_canonical([omega])[0], k, 2)
+    log_n1 = sharding.four_step_split(k, world)
+    n1, n2 = 1 << log_n1, 1 << (k - log_n1)
+    rows = [zk.DeviceColumn((n1 // world) * n2) for _ in range(world)]
+    cols = [zk.DeviceColumn.from_host(sharding.column_block(a, k, log_n1, world, r).reshape(-1, 4)) for r in range(world)]
+    lib = zk.load()
+    # steps 1 + 2 of every rank (the exchange is complete once all of them have stored)
+    for r in range(world):
+        ops = _OneGpuRanks(zk, k, world, r, rows)
+        ops.ntt_rows(cols[r], n2 // world, log_n1, pow(omega, n2, FR_MODULUS))
+        ops.twiddle_exchange(cols[r], k, log_n1, omega)
+    # step 3 of every rank
+    blocks = []
+    for r in range(world):
+        _OneGpuRanks(zk, k, world, r, rows).ntt_rows(rows[r], n1 // world, k - log_n1, pow(omega, n1, FR_MODULUS))
+        blocks.append(rows[r].to_host().reshape(n1 // world, n2, 4))
+    got = sharding.natural_from_row_blocks(blocks, k, log_n1)
+    assert np.array_equal(got, want)
+
+
+def test_packed_exchange_layout(zk):
+    """The NCCL form: pack per destination, then b200zk_ntt4_gather_rows_dev; world = 1 makes the
+    exchange the identity, so pack + gather must reproduce the direct row block."""
+    from b200zk import sharding
+    from b200zk.api import FR_MODULUS, FR_ROOT_OF_UNITY, _ptr, fr_limbs
+    k, world = 11, 1
+    n = 1 << k
+    a = co.gen_scalars(0x4E99, n)
+    omega = pow(FR_ROOT_OF_UNITY, 1 << (28 - k), FR_MODULUS)
+    log_n1 = sharding.four_step_split(k, world)
+    n1, n2 = 1 << log_n1, 1 << (k - log_n1)
+    lib = zk.load()
+    col = zk.DeviceColumn.from_host(sharding.column_block(a, k, log_n1, world, 0).reshape(-1, 4))
+    send, rows = zk.DeviceColumn(n), zk.DeviceColumn(n)
+    w = fr_limbs(omega)
+    zk.check(lib.b200zk_ntt_dev(C.c_void_p(col.ptr), n1, n2, log_n1, _ptr(fr_limbs(pow(omega, n2, FR_MODULUS))), None, None))
+    bases = (C.c_void_p * 1)(send.ptr)
+    zk.check(lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(col.ptr), k, log_n1, _ptr(w), 1, 0, bases, n2, 0, None))
+    zk.check(lib.b200zk_ntt4_gather_rows_dev(C.c_void_p(send.ptr), C.c_void_p(rows.ptr), k, log_n1, 1, None))
+    zk.check(lib.b200zk_ntt_dev(C.c_void_p(rows.ptr), n2, n1, k - log_n1, _ptr(fr_limbs(pow(omega, n1, FR_MODULUS))), None, None))
+    got = sharding.natural_from_row_blocks([rows.to_host().reshape(n1, n2, 4)], k, log_n1)
+    want = co.best_fft(a.copy(), bn.fr_array_from_canonical([omega])[0], k, 2)
+    assert np.array_equal(got, want)
+
+
+def test_bad_split_is_rejected(zk):
+    from b200zk.api import _ptr, fr_limbs
+    lib = zk.load()
+    col = zk.DeviceColumn(16)
+    bases = (C.c_void_p * 1)(col.ptr)
+    rc = lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(col.ptr), 4, 2, _ptr(fr_limbs(1)), 3, 0, bases, 4, 0, None)
+    assert rc != 0 and b"world" in lib.b200zk_last_error()

@@ -26,6 +26,49 @@ def test_shard_range_covers_everything():
     assert cols == list(range(11))
 
 
+class _CpuFourStep:
+    """Oracle stand-ins for the device steps of sharded_best_fft + a gloo all-to-all."""
+
+    def __init__(self, dist, bn, co, world, rank):
+        self.dist, self.bn, self.co, self.world, self.rank = dist, bn, co, world, rank
+
+    def ntt_rows(self, buf, count, log_len, omega):
+        w = self.bn.fr_array_from_canonical([omega])[0]
+        for i in range(count):
+            buf[i] = self.co.best_fft(np.ascontiguousarray(buf[i]), w, log_len, 1)
+
+    def twiddle_exchange(self, buf, k, log_n1, omega):
+        import torch
+        bn, world, rank = self.bn, self.world, self.rank
+        n1, n2 = 1 << log_n1, 1 << (k - log_n1)
+        m, rows = n2 // world, n1 // world
+        vals = [bn.fr_array_to_canonical(buf[jl]) for jl in range(m)]
+        send = np.zeros((world, rows, m, 4), dtype=np.uint64)
+        for jl in range(m):
+            tw = [v * pow(omega, i1 * (rank * m + jl), bn.R) % bn.R for i1, v in enumerate(vals[jl])]
+            send[:, :, jl] = bn.fr_array_from_canonical(tw).reshape(world, rows, 4)
+        recv = torch.empty_like(torch.from_numpy(send.view(np.int64)))
+        self.dist.all_to_all_single(recv, torch.from_numpy(send.view(np.int64)))
+        recv = recv.numpy().view(np.uint64)                       # [r][il][jl]
+        return np.ascontiguousarray(recv.transpose(1, 0, 2, 3)).reshape(rows, n2, 4)
+
+
+def _four_step_check(rank, world, dist, sharding, bn, co):
+    import torch
+    k = 8
+    a = co.gen_scalars(11, 1 << k)
+    omega = pow(bn.FR_ROOT_OF_UNITY, 1 << (28 - k), bn.R)
+    log_n1 = sharding.four_step_split(k, world)
+    x = sharding.column_block(a, k, log_n1, world, rank)
+    rows = sharding.sharded_best_fft(x, k, omega, _CpuFourStep(dist, bn, co, world, rank), world, rank)
+    t = torch.from_numpy(np.ascontiguousarray(rows).view(np.int64))
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    got = sharding.natural_from_row_blocks([o.numpy().view(np.uint64) for o in outs], k, log_n1)
+    want = co.best_fft(a.copy(), bn.fr_array_from_canonical([omega])[0], k, 1)
+    return bool(np.array_equal(got, want))
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "anon-aadhaar-halo2_b200"))
@@ -56,7 +99,8 @@ def _worker(rank, world, port, q):
         b, e = sharding.shard_range(size, rank, world)
         full = sharding.gather_extended_chunks(col[b:e].copy(), size)
         ok_h = np.array_equal(full, col)
-        q.put((rank, ok_msm, ok_h))
+        ok_fft = _four_step_check(rank, world, dist, sharding, bn, co)
+        q.put((rank, ok_msm, ok_h and ok_fft))
     finally:
         dist.destroy_process_group()
 
