@@ -31,3 +31,11 @@ from .quotient import (  # noqa: F401,E402
     LookupCommitted,
     ProvingKeyCosets,
 )
+from .prover_steps import (  # noqa: F401,E402
+    batch_invert,
+    eval_polynomial,
+    eval_polynomial_many,
+    kate_division,
+    lookup_products,
+    permutation_products,
+)

@@ -81,6 +81,13 @@ def load() -> C.CDLL:
         "b200zk_quotient_graph": ([vp, vp, u64, u64], C.c_int),
         "b200zk_quotient_permutation": ([vp, u64, vp, vp, vp, u32, vp, u32, u32, u32, u64, u64, u64, vp, vp, vp], C.c_int),
         "b200zk_quotient_lookup": ([vp, u64, u64, u64, u64, u64, u64, u64, u64], C.c_int),
+        "b200zk_batch_invert": ([vp, sz], C.c_int),
+        "b200zk_batch_invert_dev": ([vp, sz, vp], C.c_int),
+        "b200zk_prefix_product_dev": ([vp, sz, vp, sz, sz, sz, vp, vp], C.c_int),
+        "b200zk_permutation_product_dev": ([vp, vp, u32, u32, u32, vp, vp, vp, vp, u32, vp, vp, vp], C.c_int),
+        "b200zk_lookup_product_dev": ([vp, vp, vp, vp, u32, u32, vp, vp, u32, vp, vp, vp], C.c_int),
+        "b200zk_eval_polynomial_dev": ([vp, sz, sz, sz, vp, vp, vp], C.c_int),
+        "b200zk_kate_division_dev": ([vp, sz, vp, vp, vp], C.c_int),
         "b200zk_gen_scalars_dev": ([vp, sz, u64, sz], C.c_int),
         "b200zk_gen_points_dev": ([vp, sz, u64, sz], C.c_int),
         "b200zk_modmul_peak": ([u32, C.POINTER(C.c_double)], C.c_int),

@@ -216,6 +216,51 @@ int b200zk_quotient_lookup(const b200zk_quotient_env* env, uint64_t values_handl
                            uint64_t permuted_table_handle, uint64_t l0_handle, uint64_t l_last_handle,
                            uint64_t l_active_row_handle);
 
+/* ---- column arithmetic around the commitments (SURVEY.md section 8 f) ------------------- */
+/* ff 0.12 `BatchInvert::batch_invert` (reference Cargo.lock:339-341): a[i] <- a[i]^-1 in place,
+ * zeros stay zero. */
+int b200zk_batch_invert(uint64_t* a, size_t n);
+int b200zk_batch_invert_dev(void* d_a, size_t n, void* stream);
+
+/* out[c][0] = first[c] (1 when null), out[c][i] = out[c][i-1] * in[c][i-1] for `count` columns of
+ * n elements: the running products of the permutation and lookup arguments.  `first` is a host
+ * array of count x 4 limbs.  `d_out` may equal `d_in`. */
+int b200zk_prefix_product_dev(const void* d_in, size_t in_stride, void* d_out, size_t out_stride, size_t count,
+                              size_t n, const uint64_t* first_or_null, void* stream);
+
+/* halo2_proofs/src/plonk/permutation/prover.rs `Argument::commit`, the arithmetic of every set:
+ * for chunks of `chunk_len` columns, modified[i] = prod_col (v_col[i] + delta^j beta omega^i + gamma)
+ * / prod_col (v_col[i] + beta sigma_col[i] + gamma) (j = column index over the whole argument), then
+ * z_s[0] = z_{s-1}[n - blinding_factors - 1] (1 for the first set), z_s[i+1] = z_s[i] * modified[i].
+ * d_values / d_sigma: host arrays of n_cols device pointers to Lagrange-basis columns of 2^k
+ * elements (column values and pkey.permutations).  d_z receives ceil(n_cols / chunk_len) columns
+ * of 2^k elements.  Upstream overwrites the last `blinding_factors` rows of each z with
+ * `Scalar::random(rng)`: pass those scalars (sets x blinding_factors x 4 limbs, host) in `blinds`
+ * so the caller's RNG stream is the one consumed, or null to leave the computed values. */
+int b200zk_permutation_product_dev(const void* const* d_values, const void* const* d_sigma, uint32_t n_cols,
+                                   uint32_t chunk_len, uint32_t k, const uint64_t beta[4], const uint64_t gamma[4],
+                                   const uint64_t omega[4], const uint64_t delta[4], uint32_t blinding_factors,
+                                   const uint64_t* blinds_or_null, void* d_z, void* stream);
+
+/* halo2_proofs/src/plonk/lookup/prover.rs `Permuted::commit_product` for `count` lookups:
+ * z[0] = 1, z[i+1] = z[i] * (compressed_input[i] + beta)(compressed_table[i] + gamma)
+ *                         / ((permuted_input[i] + beta)(permuted_table[i] + gamma)),
+ * last `blinding_factors` rows from `blinds` (count x blinding_factors x 4 limbs) when given. */
+int b200zk_lookup_product_dev(const void* const* d_compressed_input, const void* const* d_compressed_table,
+                              const void* const* d_permuted_input, const void* const* d_permuted_table,
+                              uint32_t count, uint32_t k, const uint64_t beta[4], const uint64_t gamma[4],
+                              uint32_t blinding_factors, const uint64_t* blinds_or_null, void* d_z, void* stream);
+
+/* halo2_proofs/src/arithmetic.rs `eval_polynomial(poly, point)` for `count` polynomials of n
+ * coefficients (polynomial c at d_polys + c * stride), each at its own point (host, count x 4
+ * limbs); results to host memory `out` (count x 4 limbs). */
+int b200zk_eval_polynomial_dev(const void* d_polys, size_t stride, size_t count, size_t n, const uint64_t* points,
+                               uint64_t* out, void* stream);
+
+/* halo2_proofs/src/arithmetic.rs `kate_division(a, b)`: quotient of a(X) (n coefficients) by
+ * (X - b), n - 1 coefficients to d_q (the remainder a(b) is dropped, as upstream). */
+int b200zk_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q, void* stream);
+
 /* ---- synthetic inputs (benchmark / test support; oracle/bn254.py defines the streams) -- */
 int b200zk_gen_scalars_dev(void* d_out, size_t n, uint64_t seed, size_t start);
 int b200zk_gen_points_dev(void* d_out, size_t n, uint64_t seed, size_t start);

@@ -78,11 +78,12 @@ def test_packed_exchange_layout(zk):
     col = zk.DeviceColumn.from_host(sharding.column_block(a, k, log_n1, world, 0).reshape(-1, 4))
     send, rows = zk.DeviceColumn(n), zk.DeviceColumn(n)
     w = fr_limbs(omega)
-    zk.check(lib.b200zk_ntt_dev(C.c_void_p(col.ptr), n1, n2, log_n1, _ptr(fr_limbs(pow(omega, n2, FR_MODULUS))), None, None))
+    w1, w2 = fr_limbs(pow(omega, n2, FR_MODULUS)), fr_limbs(pow(omega, n1, FR_MODULUS))   # kept alive across the calls
+    zk.check(lib.b200zk_ntt_dev(C.c_void_p(col.ptr), n1, n2, log_n1, _ptr(w1), None, None))
     bases = (C.c_void_p * 1)(send.ptr)
     zk.check(lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(col.ptr), k, log_n1, _ptr(w), 1, 0, bases, n2, 0, None))
     zk.check(lib.b200zk_ntt4_gather_rows_dev(C.c_void_p(send.ptr), C.c_void_p(rows.ptr), k, log_n1, 1, None))
-    zk.check(lib.b200zk_ntt_dev(C.c_void_p(rows.ptr), n2, n1, k - log_n1, _ptr(fr_limbs(pow(omega, n1, FR_MODULUS))), None, None))
+    zk.check(lib.b200zk_ntt_dev(C.c_void_p(rows.ptr), n2, n1, k - log_n1, _ptr(w2), None, None))
     got = sharding.natural_from_row_blocks([rows.to_host().reshape(n1, n2, 4)], k, log_n1)
     want = co.best_fft(a.copy(), bn.fr_array_from_canonical([omega])[0], k, 2)
     assert np.array_equal(got, want)
@@ -93,5 +94,6 @@ def test_bad_split_is_rejected(zk):
     lib = zk.load()
     col = zk.DeviceColumn(16)
     bases = (C.c_void_p * 1)(col.ptr)
-    rc = lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(col.ptr), 4, 2, _ptr(fr_limbs(1)), 3, 0, bases, 4, 0, None)
+    w = fr_limbs(1)
+    rc = lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(col.ptr), 4, 2, _ptr(w), 3, 0, bases, 4, 0, None)
     assert rc != 0 and b"world" in lib.b200zk_last_error()

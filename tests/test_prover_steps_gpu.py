@@ -1,0 +1,111 @@
+"""GPU parity of the prover steps either side of the hot path (csrc/poly.cu) through the C ABI
+against oracle/prover_steps_cpu.py on the same seeded inputs, bit-exact; sizes cross every
+tile boundary of the kernels (2048-element tiles, 8 elements per thread)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as bn
+from oracle import c_oracle as co
+from oracle import prover_steps_cpu as ps
+
+pytestmark = pytest.mark.gpu
+
+R = bn.R
+F = bn.fr_array_from_canonical
+I = bn.fr_array_to_canonical
+
+
+@pytest.mark.parametrize("n", [1, 7, 2048, 2049, 5000, 20000, (1 << 17) + 3])
+def test_batch_invert(zk, n):
+    a = co.gen_scalars(0xB1 + n, n)
+    a[n // 2] = 0
+    if n > 10:
+        a[0] = 0
+        a[n - 1] = 0
+    got = a.copy()
+    zk.batch_invert(got)
+    ai, gi = I(a), I(got)
+    # a * a^-1 == 1 (the inverse is unique) and zeros stay zero; spot-check against pow()
+    for x, y in list(zip(ai, gi))[:: max(1, n // 500)]:
+        assert (x == 0 and y == 0) or x * y % R == 1
+    assert gi[n // 2] == 0
+    if n <= 5000:
+        assert gi == ps.batch_invert(ai)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 2048, 2049, 4097, 1 << 15, (1 << 15) + 77])
+def test_eval_polynomial(zk, n):
+    rnd = random.Random(n)
+    poly = co.gen_scalars(0xE0 + n, max(n, 1))[:n]
+    x = rnd.randrange(R)
+    got = zk.eval_polynomial(poly, x)
+    assert I(got[None, :])[0] == ps.eval_polynomial(I(poly), x)
+
+
+def test_eval_polynomial_batch_of_points(zk):
+    rnd = random.Random(9)
+    count, n = 37, 3000
+    polys = co.gen_scalars(0xE9, count * n).reshape(count, n, 4)
+    pts = [rnd.randrange(R) for _ in range(count)]
+    pts[0], pts[1] = 0, 1
+    got = I(zk.eval_polynomial_many(polys, pts))
+    assert got == [ps.eval_polynomial(I(polys[c]), pts[c]) for c in range(count)]
+
+
+@pytest.mark.parametrize("n", [1, 2, 9, 2048, 2049, 6145, (1 << 15), (1 << 15) + 5])
+def test_kate_division(zk, n):
+    rnd = random.Random(n + 1)
+    a = co.gen_scalars(0xCA + n, n)
+    for b in (rnd.randrange(R), 0, 1):
+        got = zk.kate_division(a, b)
+        assert got.shape == (n - 1, 4)
+        assert I(got) == ps.kate_division(I(a), b)
+
+
+@pytest.mark.parametrize("k,n_cols,chunk,bf", [(4, 5, 2, 3), (6, 7, 3, 5), (12, 9, 2, 5), (13, 4, 1, 5)])
+def test_permutation_products(zk, k, n_cols, chunk, bf):
+    n = 1 << k
+    rnd = random.Random(k)
+    values = [co.gen_scalars(0x70 + j, n) for j in range(n_cols)]
+    sigma = [co.gen_scalars(0x90 + j, n) for j in range(n_cols)]
+    beta, gamma = rnd.randrange(R), rnd.randrange(R)
+    n_sets = -(-n_cols // chunk)
+    blinds = [[rnd.randrange(R) for _ in range(bf)] for _ in range(n_sets)]
+    omega = pow(bn.FR_ROOT_OF_UNITY, 1 << (28 - k), R)
+    want = ps.permutation_products([I(v) for v in values], [I(s) for s in sigma], chunk, omega, beta, gamma, bf, blinds)
+    got = zk.permutation_products(values, sigma, chunk, k, beta, gamma, bf, np.stack([F(b) for b in blinds]))
+    assert got.shape == (n_sets, n, 4)
+    for s in range(n_sets):
+        assert I(got[s]) == want[s], f"set {s}"
+    # without blinds the computed rows are kept
+    want = ps.permutation_products([I(v) for v in values], [I(s) for s in sigma], chunk, omega, beta, gamma, bf)
+    got = zk.permutation_products(values, sigma, chunk, k, beta, gamma, bf)
+    assert [I(g) for g in got] == want
+
+
+def test_permutation_product_identity_permutation_is_all_ones(zk):
+    k, n_cols = 10, 5
+    n = 1 << k
+    omega = pow(bn.FR_ROOT_OF_UNITY, 1 << (28 - k), R)
+    values = [co.gen_scalars(0x50 + j, n) for j in range(n_cols)]
+    ident = [F([pow(bn.FR_DELTA, j, R) * pow(omega, i, R) % R for i in range(n)]) for j in range(n_cols)]
+    got = zk.permutation_products(values, ident, 2, k, 12345, 67890, 5)
+    assert all(I(g) == [1] * n for g in got)
+
+
+@pytest.mark.parametrize("k,count,bf", [(4, 1, 3), (11, 3, 5), (12, 2, 5)])
+def test_lookup_products(zk, k, count, bf):
+    n = 1 << k
+    rnd = random.Random(k * 7)
+    cols = [[co.gen_scalars(0x30 + 16 * g + j, n) for j in range(count)] for g in range(4)]
+    beta, gamma = rnd.randrange(R), rnd.randrange(R)
+    blinds = [[rnd.randrange(R) for _ in range(bf)] for _ in range(count)]
+    got = zk.lookup_products(cols[0], cols[1], cols[2], cols[3], k, beta, gamma, bf, np.stack([F(b) for b in blinds]))
+    for j in range(count):
+        want = ps.lookup_product(I(cols[0][j]), I(cols[1][j]), I(cols[2][j]), I(cols[3][j]), beta, gamma, bf, blinds[j])
+        assert I(got[j]) == want, f"lookup {j}"
+    got = zk.lookup_products(cols[0], cols[1], cols[2], cols[3], k, beta, gamma, bf)
+    want = ps.lookup_product(I(cols[0][0]), I(cols[1][0]), I(cols[2][0]), I(cols[3][0]), beta, gamma, bf)
+    assert I(got[0]) == want
