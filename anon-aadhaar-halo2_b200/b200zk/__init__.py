@@ -18,7 +18,11 @@ from .api import (  # noqa: F401
     ParamsKZG,
     best_fft,
     best_multiexp,
+    g1_affine_from_bytes,
+    g1_affine_to_bytes,
     g1_sum,
+    g1_to_bytes,
+    g1_to_evm_bytes,
     init,
     kernel_launches,
     modmul_peak,

@@ -88,6 +88,10 @@ def load() -> C.CDLL:
         "b200zk_lookup_product_dev": ([vp, vp, vp, vp, u32, u32, vp, vp, u32, vp, vp, vp], C.c_int),
         "b200zk_eval_polynomial_dev": ([vp, sz, sz, sz, vp, vp, vp], C.c_int),
         "b200zk_kate_division_dev": ([vp, sz, vp, vp, vp], C.c_int),
+        "b200zk_g1_to_bytes": ([vp, sz, vp], C.c_int),
+        "b200zk_g1_affine_to_bytes": ([vp, sz, vp], C.c_int),
+        "b200zk_g1_to_evm_bytes": ([vp, sz, vp], C.c_int),
+        "b200zk_g1_affine_from_bytes": ([vp, sz, vp], C.c_int),
         "b200zk_gen_scalars_dev": ([vp, sz, u64, sz], C.c_int),
         "b200zk_gen_points_dev": ([vp, sz, u64, sz], C.c_int),
         "b200zk_modmul_peak": ([u32, C.POINTER(C.c_double)], C.c_int),

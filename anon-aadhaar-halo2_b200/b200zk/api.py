@@ -253,3 +253,38 @@ class ParamsKZG:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------- halo2curves derive/curve.rs
+def g1_to_bytes(points: np.ndarray) -> np.ndarray:
+    """`G1Affine::from(p).to_bytes()` for Jacobian results (count, 12) -> (count, 32) uint8."""
+    _check_vec(points, 12, "points")
+    out = np.zeros((points.shape[0], 32), dtype=np.uint8)
+    check(load().b200zk_g1_to_bytes(_ptr(points), points.shape[0], _ptr(out)))
+    return out
+
+
+def g1_affine_to_bytes(points: np.ndarray) -> np.ndarray:
+    """`G1Affine::to_bytes` for (count, 8) affine points (what `ParamsKZG::write` emits)."""
+    _check_vec(points, 8, "points")
+    out = np.zeros((points.shape[0], 32), dtype=np.uint8)
+    check(load().b200zk_g1_affine_to_bytes(_ptr(points), points.shape[0], _ptr(out)))
+    return out
+
+
+def g1_to_evm_bytes(points: np.ndarray) -> np.ndarray:
+    """The 64-byte big-endian (x, y) encoding of the EVM transcript / calldata."""
+    _check_vec(points, 12, "points")
+    out = np.zeros((points.shape[0], 64), dtype=np.uint8)
+    check(load().b200zk_g1_to_evm_bytes(_ptr(points), points.shape[0], _ptr(out)))
+    return out
+
+
+def g1_affine_from_bytes(data: np.ndarray) -> np.ndarray:
+    """`G1Affine::from_bytes` for (count, 32) uint8 -> (count, 8); raises on an invalid point
+    (upstream returns CtOption::none, which `ParamsKZG::read` unwraps)."""
+    assert isinstance(data, np.ndarray) and data.dtype == np.uint8 and data.ndim == 2 and data.shape[1] == 32
+    data = np.ascontiguousarray(data)
+    out = np.zeros((data.shape[0], 8), dtype=np.uint64)
+    check(load().b200zk_g1_affine_from_bytes(_ptr(data), data.shape[0], _ptr(out)))
+    return out

@@ -104,6 +104,7 @@ struct Context {
     std::map<uint64_t, DevBuffer> buffers;  // device-resident Fr columns (b200zk_dev_*)
     Arena quot_graph, quot_ptrs;
     Arena poly_work, poly_small, poly_cols, poly_scan;   // csrc/poly.cu scratch
+    Arena enc_io;                                          // csrc/encoding.cu staging
     uint64_t next_handle = 1;
 };
 

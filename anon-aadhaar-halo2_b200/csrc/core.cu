@@ -157,7 +157,7 @@ int b200zk_shutdown(void) {
         ntt_release_tables(c);
         msm_release_bases(c);
         for (Arena* a : {&c.ntt_io, &c.ntt_tmp, &c.ntt_aux, &c.msm_scalars, &c.msm_bases, &c.msm_work, &c.msm_carry, &c.misc, &c.quot_graph, &c.quot_ptrs,
-                         &c.poly_work, &c.poly_small, &c.poly_cols, &c.poly_scan})
+                         &c.poly_work, &c.poly_small, &c.poly_cols, &c.poly_scan, &c.enc_io})
             a->release();
         for (auto& kv : c.buffers)
             if (kv.second.owned) cudaFree(kv.second.p);

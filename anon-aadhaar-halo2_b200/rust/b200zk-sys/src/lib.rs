@@ -69,6 +69,11 @@ extern "C" {
     pub fn b200zk_eval_polynomial_dev(d_polys: *const c_void, stride: usize, count: usize, n: usize, points: *const u64, out: *mut u64, stream: *mut c_void) -> c_int;
     pub fn b200zk_kate_division_dev(d_a: *const c_void, n: usize, b: *const u64, d_q: *mut c_void, stream: *mut c_void) -> c_int;
 
+    pub fn b200zk_g1_to_bytes(points_xyz: *const u64, count: usize, out32: *mut u8) -> c_int;
+    pub fn b200zk_g1_affine_to_bytes(points_xy: *const u64, count: usize, out32: *mut u8) -> c_int;
+    pub fn b200zk_g1_to_evm_bytes(points_xyz: *const u64, count: usize, out64: *mut u8) -> c_int;
+    pub fn b200zk_g1_affine_from_bytes(in32: *const u8, count: usize, points_xy: *mut u64) -> c_int;
+
     pub fn b200zk_dev_alloc(n_elems: usize, handle_out: *mut u64) -> c_int;
     pub fn b200zk_dev_free(handle: u64) -> c_int;
     pub fn b200zk_dev_view(parent: u64, offset: usize, n_elems: usize, handle_out: *mut u64) -> c_int;

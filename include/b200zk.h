@@ -261,6 +261,21 @@ int b200zk_eval_polynomial_dev(const void* d_polys, size_t stride, size_t count,
  * (X - b), n - 1 coefficients to d_q (the remainder a(b) is dropped, as upstream). */
 int b200zk_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q, void* stream);
 
+/* ---- wire formats of G1 points (SURVEY.md section 8 f, rank 3) ---------------------------- */
+/* halo2curves 0.3.1 src/derive/curve.rs `G1Affine::to_bytes` applied to `count` points: 32 bytes
+ * each, x little-endian canonical with the parity of y in bit 7 of byte 31, identity = zeros.
+ * `points_xyz`: Jacobian G1 (12 limbs each, e.g. MSM results; normalised on the device);
+ * `points_xy`: G1Affine (8 limbs each, e.g. ParamsKZG::g for `ParamsKZG::write`). */
+int b200zk_g1_to_bytes(const uint64_t* points_xyz, size_t count, uint8_t* out32);
+int b200zk_g1_affine_to_bytes(const uint64_t* points_xy, size_t count, uint8_t* out32);
+/* The EVM transcript / calldata encoding (reference solidity_verifier_contract/contract.sol:77-87):
+ * 64 bytes per point, x then y big-endian canonical; identity = zeros. */
+int b200zk_g1_to_evm_bytes(const uint64_t* points_xyz, size_t count, uint8_t* out64);
+/* `G1Affine::from_bytes` for `count` points (the decompression `ParamsKZG::read` performs for
+ * every SRS point: one square root each).  Fails, naming the first offending index, when an x
+ * is not canonical or not on the curve. */
+int b200zk_g1_affine_from_bytes(const uint8_t* in32, size_t count, uint64_t* points_xy);
+
 /* ---- synthetic inputs (benchmark / test support; oracle/bn254.py defines the streams) -- */
 int b200zk_gen_scalars_dev(void* d_out, size_t n, uint64_t seed, size_t start);
 int b200zk_gen_points_dev(void* d_out, size_t n, uint64_t seed, size_t start);

@@ -307,3 +307,40 @@ def seeded_g1_points(seed: int, n: int, start: int = 0) -> list:
             j += 1
         out.append(_jac_to_affine(acc))
     return out
+
+
+# ----------------------------------------------------------------------- wire formats
+# [DEP] halo2curves 0.3.1 src/derive/curve.rs `new_curve_impl!` (reference Cargo.lock:484-486):
+# to_bytes = x little-endian, bit 7 of byte 31 = parity of the canonical y, identity = zeros.
+def g1_to_bytes(p) -> bytes:
+    if p is None:
+        return bytes(32)
+    b = bytearray(p[0].to_bytes(32, "little"))
+    b[31] |= (p[1] & 1) << 7
+    return bytes(b)
+
+
+def g1_from_bytes(b: bytes):
+    """Inverse of g1_to_bytes; raises ValueError for a non-canonical x or a non-residue."""
+    b = bytearray(b)
+    sign = b[31] >> 7
+    b[31] &= 0x7F
+    x = int.from_bytes(b, "little")
+    if x == 0 and sign == 0:
+        return None
+    if x >= Q:
+        raise ValueError("x coordinate is not canonical")
+    rhs = (x * x * x + 3) % Q
+    y = pow(rhs, (Q + 1) // 4, Q)
+    if y * y % Q != rhs:
+        raise ValueError("not on the curve")
+    if (y & 1) != sign:
+        y = Q - y
+    return (x, y)
+
+
+def g1_to_evm_bytes(p) -> bytes:
+    """reference solidity_verifier_contract/contract.sol:77-87: x then y, 32-byte big-endian."""
+    if p is None:
+        return bytes(64)
+    return p[0].to_bytes(32, "big") + p[1].to_bytes(32, "big")
