@@ -117,12 +117,14 @@ __global__ void msm_hist_kernel(const Fr* __restrict__ scalars, size_t scalar_st
                                 uint32_t nwin, uint32_t key_windows, uint32_t* __restrict__ hist,
                                 int32_t* __restrict__ digits) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const bool valid = i < n;                     // no early return: the warp votes below need every lane
     const uint32_t col = blockIdx.y;
-    const Fr s = ldg_fr(scalars + (size_t)col * scalar_stride + i).from_mont();
+    Fr s = Fr::zero();
+    if (valid) s = ldg_fr(scalars + (size_t)col * scalar_stride + i).from_mont();
     const uint32_t nb = 1u << (c - 1);
     const uint32_t half = 1u << (c - 1);
     const uint32_t mask = (1u << c) - 1u;
+    const uint32_t lane = threadIdx.x & 31u;
     uint32_t carry = 0;
     for (uint32_t w = 0; w < nwin; ++w) {
         const uint32_t o = w * c;
@@ -136,11 +138,16 @@ __global__ void msm_hist_kernel(const Fr* __restrict__ scalars, size_t scalar_st
         int32_t sd;
         if (d > half) { sd = (int32_t)d - (int32_t)(1u << c); carry = 1; }
         else { sd = (int32_t)d; carry = 0; }
-        digits[((size_t)col * nwin + w) * n + i] = sd;
-        if (sd != 0) {
-            const uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
+        if (valid) digits[((size_t)col * nwin + w) * n + i] = sd;
+        // One atomic per distinct key in the warp: witness columns are full of repeated values
+        // (all-equal scalars put every point of a window in one bucket), and same-address
+        // atomics serialise.
+        const uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
+        const uint32_t key = (valid && sd != 0) ? mag - 1 : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (key != 0xffffffffu && lane == (uint32_t)(__ffs(peers) - 1)) {
             const size_t group = (size_t)col * key_windows + (key_windows > 1 ? w : 0);
-            atomicAdd(hist + group * nb + (mag - 1), 1u);
+            atomicAdd(hist + group * nb + key, (uint32_t)__popc(peers));
         }
     }
 }
@@ -239,17 +246,24 @@ __global__ void msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n,
                                    uint32_t key_windows, uint32_t table_stride, uint32_t sub_bits,
                                    uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     const uint32_t cw = blockIdx.y >> sub_bits;             // col * nwin + w
     const uint32_t sub = blockIdx.y & ((1u << sub_bits) - 1u);
-    const int32_t d = __ldcs(digits + (size_t)cw * n + i);
-    if (d == 0) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int32_t d = (i < n) ? __ldcs(digits + (size_t)cw * n + i) : 0;
     const uint32_t mag = (uint32_t)(d < 0 ? -d : d);
-    if (((mag - 1) >> (c - 1 - sub_bits)) != sub) return;
+    const bool mine = d != 0 && ((mag - 1) >> (c - 1 - sub_bits)) == sub;
+    // warp-aggregated cursor bump: one atomic per distinct bucket in the warp
+    const uint32_t key = mine ? mag - 1 : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
     const uint32_t col = cw / nwin, w = cw - col * nwin;
     const uint32_t nb = 1u << (c - 1);
     const size_t group = (size_t)col * key_windows + (key_windows > 1 ? w : 0);
-    const uint32_t pos = atomicAdd(cursor + group * nb + (mag - 1), 1u);
+    uint32_t base = 0;
+    if (mine && lane == leader) base = atomicAdd(cursor + group * nb + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!mine) return;
+    const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
     sorted[pos] = ((uint32_t)i + w * table_stride) | (d < 0 ? 0x80000000u : 0u);
 }
 

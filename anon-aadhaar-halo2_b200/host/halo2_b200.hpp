@@ -183,4 +183,52 @@ class ParamsKZG {
     uint64_t h_g_ = 0, h_gl_ = 0;
 };
 
+// ---- the prover loops either side of the hot path (SURVEY.md section 8 f) --------------
+namespace detail {
+// RAII device column (b200zk_dev_* handle)
+struct DevCol {
+    uint64_t h = 0;
+    explicit DevCol(size_t n) { check(b200zk_dev_alloc(n, &h)); }
+    DevCol(const std::vector<Fr>& a) : DevCol(a.size()) {
+        if (!a.empty()) check(b200zk_dev_upload(h, 0, a.data()->data(), a.size()));
+    }
+    ~DevCol() { if (h) b200zk_dev_free(h); }
+    DevCol(const DevCol&) = delete;
+    DevCol& operator=(const DevCol&) = delete;
+    void* ptr() const { return b200zk_dev_ptr(h); }
+};
+}  // namespace detail
+
+// ff::BatchInvert: `a.iter_mut().batch_invert()`; zeros stay zero
+inline void batch_invert(std::vector<Fr>& a) {
+    if (!a.empty()) check(b200zk_batch_invert(a.data()->data(), a.size()));
+}
+
+// arithmetic.rs eval_polynomial(poly, point)
+inline Fr eval_polynomial(const std::vector<Fr>& poly, const Fr& point) {
+    Fr out{};
+    if (poly.empty()) return out;
+    detail::DevCol d(poly);
+    check(b200zk_eval_polynomial_dev(d.ptr(), poly.size(), 1, poly.size(), point.data(), out.data(), nullptr));
+    return out;
+}
+
+// arithmetic.rs kate_division(a, b): a(X) / (X - b)
+inline std::vector<Fr> kate_division(const std::vector<Fr>& a, const Fr& b) {
+    require(!a.empty(), "a.len() >= 1");
+    std::vector<Fr> q(a.size() - 1);
+    if (q.empty()) return q;
+    detail::DevCol d(a), dq(q.size());
+    check(b200zk_kate_division_dev(d.ptr(), a.size(), b.data(), dq.ptr(), nullptr));
+    check(b200zk_dev_download(dq.h, 0, q.data()->data(), q.size()));
+    return q;
+}
+
+// halo2curves G1Affine::to_bytes of Jacobian results (e.g. commitments on their way into a transcript)
+inline std::vector<std::array<uint8_t, 32>> g1_to_bytes(const std::vector<G1>& points) {
+    std::vector<std::array<uint8_t, 32>> out(points.size());
+    if (!points.empty()) check(b200zk_g1_to_bytes(points.data()->data(), points.size(), out.data()->data()));
+    return out;
+}
+
 }  // namespace halo2

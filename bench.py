@@ -576,7 +576,35 @@ def sweep(args, torch, b200zk, lib, dev) -> None:
                      "ntt_ms": ntt_ms, "ntt_alg_GBps": ntt_alg_bytes(k) / ntt_ms / 1e6,
                      "ntt_frac_of_modmul_peak": ntt_mm / peak})
         del d_scal, d_base, d_ntt
-    print(json.dumps({"sweep": rows, "modmul_peak_G_per_s": peak / 1e9}), flush=True)
+    # ---- adversarial scalar distributions (SURVEY.md section 8 d) at k = 22
+    k = 22
+    n = 1 << k
+    d_base = torch.empty(n * 8, dtype=torch.int64, device=dev)
+    d_pt = torch.zeros(12, dtype=torch.int64, device=dev)
+    b200zk.check(lib.b200zk_gen_points_dev(vp(d_base), n, SEED_P + k, 0))
+    uniform = torch.empty(n * 4, dtype=torch.int64, device=dev)
+    b200zk.check(lib.b200zk_gen_scalars_dev(vp(uniform), n, SEED_S + k, 0))
+    minus_one = torch.from_numpy(fr_limbs(-1).view(np.int64)).to(dev).repeat(n)
+    gen = torch.Generator(device=dev); gen.manual_seed(7)
+    keep = (torch.rand(n, device=dev, generator=gen) < 0.1).to(torch.int64).unsqueeze(1)
+    sparse = (uniform.view(n, 4) * keep).reshape(-1).contiguous()
+    zero_one = torch.zeros(n, 4, dtype=torch.int64, device=dev)
+    zero_one[:, :] = torch.from_numpy(fr_limbs(1).view(np.int64)).to(dev)
+    zero_one = (zero_one * (torch.rand(n, device=dev, generator=gen) < 0.5).to(torch.int64).unsqueeze(1)).reshape(-1).contiguous()
+    adversarial = {}
+    for name, sc in (("uniform", uniform), ("all_r_minus_1", minus_one), ("90pct_zero", sparse), ("bits_0_1", zero_one)):
+        with torch.cuda.stream(stream):
+            b200zk.check(lib.b200zk_msm_g1_dev_async(vp(sc), vp(d_base), n, vp(d_pt), st))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                b200zk.check(lib.b200zk_msm_g1_dev_async(vp(sc), vp(d_base), n, vp(d_pt), st))
+            e1.record(stream)
+            torch.cuda.synchronize()
+        adversarial[name] = {"msm_ms": e0.elapsed_time(e1) / 3}
+    print(json.dumps({"sweep": rows, "modmul_peak_G_per_s": peak / 1e9,
+                      "adversarial_scalars_k22": adversarial}), flush=True)
 
 
 if __name__ == "__main__":
