@@ -181,6 +181,7 @@ ZK_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 // ------------------------------------------------------------------------ the field
 template <class P>
 struct alignas(16) Fp {
+    using Params = P;
     uint32_t l[8];
 
     static ZK_HD void modulus(uint32_t* m) {
