@@ -61,6 +61,19 @@ __device__ __forceinline__ Fq ldg_fq(const Fq* p) {
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
+// 64-byte points gathered at random: ask L2 to fetch exactly the two sectors of the point
+// (the default promotion pulls the whole 128-byte line, i.e. the neighbouring point as well).
+__device__ __forceinline__ Fq ldg_fq_64B(const Fq* p) {
+    uint4 a, b;
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(reinterpret_cast<const uint4*>(p) + 1));
+    Fq r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
 __device__ __forceinline__ Fq ld_fq(const Fq* p) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
     uint4 a = q[0], b = q[1];
@@ -300,16 +313,16 @@ __global__ void __launch_bounds__(128) msm_accum_kernel(const G1Affine* __restri
     // software prefetch of the next point
     uint32_t e = __ldg(sorted + begin);
     G1Affine nxt;
-    nxt.x = ldg_fq(&bases[e & 0x7fffffffu].x);
-    nxt.y = ldg_fq(&bases[e & 0x7fffffffu].y);
+    nxt.x = ldg_fq_64B(&bases[e & 0x7fffffffu].x);
+    nxt.y = ldg_fq_64B(&bases[e & 0x7fffffffu].y);
 #pragma unroll 1
     for (uint32_t pos = begin; pos < end; ++pos) {
         G1Affine p = nxt;
         const bool negate = (e >> 31) != 0;
         if (pos + 1 < end) {
             e = __ldg(sorted + pos + 1);
-            nxt.x = ldg_fq(&bases[e & 0x7fffffffu].x);
-            nxt.y = ldg_fq(&bases[e & 0x7fffffffu].y);
+            nxt.x = ldg_fq_64B(&bases[e & 0x7fffffffu].x);
+            nxt.y = ldg_fq_64B(&bases[e & 0x7fffffffu].y);
         }
         if (pos >= run_end) {
             st_xyzz(buckets + key, acc);
