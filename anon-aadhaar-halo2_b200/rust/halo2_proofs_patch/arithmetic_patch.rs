@@ -115,3 +115,59 @@ impl<G: Group> EvaluationDomain<G> {
 // calls b200zk_quotient_graph, b200zk_quotient_permutation and b200zk_quotient_lookup in upstream's
 // loop order; the result is downloaded into `values` (or kept resident for vanishing::construct,
 // which then calls b200zk_extended_to_coeff_dev with t_evaluations fused).
+
+// ---- the loops either side of the hot path (SURVEY.md section 8 f) ---------------------------
+
+/// `arithmetic::eval_polynomial` — signature unchanged; bn256::Fr goes to the device.
+pub fn eval_polynomial<F: Field>(poly: &[F], point: F) -> F {
+    if TypeId::of::<F>() == TypeId::of::<Fr>() && poly.len() >= (1 << 12) {
+        let mut h = 0u64;
+        let mut out = [0u64; 4];
+        unsafe {
+            ffi::check(ffi::b200zk_dev_alloc(poly.len(), &mut h));
+            ffi::check(ffi::b200zk_dev_upload(h, 0, poly.as_ptr() as *const u64, poly.len()));
+            ffi::check(ffi::b200zk_eval_polynomial_dev(ffi::b200zk_dev_ptr(h), poly.len(), 1, poly.len(),
+                                                       &point as *const _ as *const u64, out.as_mut_ptr(), std::ptr::null_mut()));
+            ffi::check(ffi::b200zk_dev_free(h));
+            return transmute_copy::<[u64; 4], F>(&out);
+        }
+    }
+    upstream::eval_polynomial(poly, point)
+}
+
+/// `arithmetic::kate_division` — a(X) / (X - b), signature unchanged.
+pub fn kate_division<'a, F: Field, I: IntoIterator<Item = &'a F>>(a: I, b: F) -> Vec<F>
+where
+    I::IntoIter: DoubleEndedIterator + ExactSizeIterator,
+{
+    let a: Vec<F> = a.into_iter().copied().collect();
+    if TypeId::of::<F>() == TypeId::of::<Fr>() && a.len() >= (1 << 12) {
+        let mut q = vec![F::zero(); a.len() - 1];
+        let (mut ha, mut hq) = (0u64, 0u64);
+        unsafe {
+            ffi::check(ffi::b200zk_dev_alloc(a.len(), &mut ha));
+            ffi::check(ffi::b200zk_dev_alloc(q.len(), &mut hq));
+            ffi::check(ffi::b200zk_dev_upload(ha, 0, a.as_ptr() as *const u64, a.len()));
+            ffi::check(ffi::b200zk_kate_division_dev(ffi::b200zk_dev_ptr(ha), a.len(), &b as *const _ as *const u64,
+                                                     ffi::b200zk_dev_ptr(hq), std::ptr::null_mut()));
+            ffi::check(ffi::b200zk_dev_download(hq, 0, q.as_mut_ptr() as *mut u64, q.len()));
+            ffi::check(ffi::b200zk_dev_free(ha));
+            ffi::check(ffi::b200zk_dev_free(hq));
+        }
+        return q;
+    }
+    upstream::kate_division(&a, b)
+}
+
+/// The `modified_values.batch_invert()` / `lookup_product.iter_mut().batch_invert()` calls of the
+/// permutation and lookup provers (ff::BatchInvert), specialised for slices of bn256::Fr.
+pub fn batch_invert_fr(values: &mut [Fr]) {
+    ffi::check(unsafe { ffi::b200zk_batch_invert(values.as_mut_ptr() as *mut u64, values.len()) });
+}
+
+/// `G1Affine::from(point).to_bytes()` for a batch of commitments on their way into the transcript.
+pub fn g1_to_bytes(points: &[G1]) -> Vec<[u8; 32]> {
+    let mut out = vec![[0u8; 32]; points.len()];
+    ffi::check(unsafe { ffi::b200zk_g1_to_bytes(points.as_ptr() as *const u64, points.len(), out.as_mut_ptr() as *mut u8) });
+    out
+}
