@@ -114,6 +114,54 @@ def test_msm_full_size_linearity(zk, k):
     assert jac_affine(out) == bn.g1_mul(bn.G1_GEN, scalar)
 
 
+def _dot_mod_r(s_limbs: np.ndarray, t: np.ndarray) -> int:
+    """sum_i s_i * t_i for s (n, 4) u64 limbs and t (n,) u64, exactly, without a Python loop over
+    n: 32-bit pieces of s against 16-bit pieces of t, 65536 rows at a time (48-bit products, so a
+    block sum stays below 2^64)."""
+    n = s_limbs.shape[0]
+    s32 = np.ascontiguousarray(s_limbs).view(np.uint32).reshape(n, 8).astype(np.uint64)
+    t16 = np.ascontiguousarray(t).view(np.uint16).reshape(n, 4).astype(np.uint64)
+    total = 0
+    for lo in range(0, n, 1 << 16):
+        m = s32[lo:lo + (1 << 16)].T @ t16[lo:lo + (1 << 16)]          # (8, 4) exact in uint64
+        for a in range(8):
+            for b in range(4):
+                total += int(m[a, b]) << (32 * a + 16 * b)
+    return total
+
+
+def test_commit_at_benchmark_size_matches_known_discrete_logs(zk):
+    """The exact configuration bench.py times — 2^24 registered points with the window table
+    (c = 22, shared bucket set), device-resident scalars — against [sum s_i t_i] G computed with
+    exact integer arithmetic; the plain best_multiexp path on the same inputs must agree."""
+    import torch
+
+    lib = zk.load()
+    k = 24
+    n = 1 << k
+    ds = torch.empty(n * 4, dtype=torch.int64, device="cuda")
+    db = torch.empty(n * 8, dtype=torch.int64, device="cuda")
+    zk.check(lib.b200zk_gen_scalars_dev(C.c_void_p(ds.data_ptr()), n, 0xA11CE000 + k, 0))
+    zk.check(lib.b200zk_gen_points_dev(C.c_void_p(db.data_ptr()), n, 0xBA5E0000 + k, 0))
+    hb = db.cpu().numpy().view(np.uint64).reshape(n, 8)
+    h = C.c_uint64(0)
+    zk.check(lib.b200zk_bases_register(C.c_void_p(hb.ctypes.data), n, C.byref(h)))
+    d_out = torch.zeros(12, dtype=torch.int64, device="cuda")
+    zk.check(lib.b200zk_msm_g1_registered_dev(h.value, C.c_void_p(ds.data_ptr()), n, 1, n, C.c_void_p(d_out.data_ptr()), None))
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint64)
+    plain = np.zeros(12, dtype=np.uint64)
+    zk.check(lib.b200zk_msm_g1_dev(C.c_void_p(ds.data_ptr()), C.c_void_p(db.data_ptr()), n, C.c_void_p(plain.ctypes.data), None))
+    zk.check(lib.b200zk_bases_evict(h.value))
+    s = ds.cpu().numpy().view(np.uint64).reshape(n, 4)
+    with np.errstate(over="ignore"):
+        t = bn._splitmix64_np(np.uint64(((0xBA5E0000 + k) << 32) & ((1 << 64) - 1)) + np.arange(n, dtype=np.uint64)) | np.uint64(1)
+    scalar = _dot_mod_r(s, t) % bn.R * pow(1 << 256, -1, bn.R) % bn.R       # scalars are Montgomery representatives
+    want = bn.g1_mul(bn.G1_GEN, scalar)
+    assert jac_affine(got) == want
+    assert jac_affine(plain) == want
+
+
 @pytest.mark.parametrize("precompute", [True, False])
 def test_params_kzg_window_table_and_batch(zk, precompute):
     """Registered bases with / without the per-window table, single and batched commits,
