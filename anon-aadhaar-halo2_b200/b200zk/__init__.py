@@ -42,4 +42,5 @@ from .prover_steps import (  # noqa: F401,E402
     kate_division,
     lookup_products,
     permutation_products,
+    permute_expression_pairs,
 )

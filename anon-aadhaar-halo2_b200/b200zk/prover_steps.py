@@ -109,3 +109,28 @@ def lookup_products(compressed_inputs, compressed_tables, permuted_inputs, permu
             c.free()
     z.free()
     return out
+
+
+def permute_expression_pairs(inputs: np.ndarray, tables: np.ndarray, k: int, blinding_factors: int,
+                             blinds: np.ndarray = None):
+    """`lookup::prover::permute_expression_pair` for a batch of lookups: inputs / tables are
+    (count, 2^k, 4); returns (permuted_inputs, permuted_tables) of the same shape.  `blinds`
+    (count, 2, blinding_factors + 1, 4): the random scalars of the last rows (input, then table).
+    Raises B200zkError("...ConstraintSystemFailure...") when an input value is not in the table."""
+    n = 1 << k
+    assert inputs.dtype == np.uint64 and inputs.shape == tables.shape and inputs.shape[1:] == (n, 4)
+    count = inputs.shape[0]
+    din = DeviceColumn.from_host(np.ascontiguousarray(inputs).reshape(-1, 4))
+    dtb = DeviceColumn.from_host(np.ascontiguousarray(tables).reshape(-1, 4))
+    oin, otb = DeviceColumn(count * n), DeviceColumn(count * n)
+    if blinds is not None:
+        blinds = np.ascontiguousarray(blinds, dtype=np.uint64)
+        assert blinds.shape == (count, 2, blinding_factors + 1, 4)
+    try:
+        check(load().b200zk_permute_expression_pair_dev(C.c_void_p(din.ptr), C.c_void_p(dtb.ptr), n, count, k,
+                                                        blinding_factors, _ptr(blinds) if blinds is not None else None,
+                                                        C.c_void_p(oin.ptr), C.c_void_p(otb.ptr), n, None))
+        return oin.to_host().reshape(count, n, 4), otb.to_host().reshape(count, n, 4)
+    finally:
+        for c in (din, dtb, oin, otb):
+            c.free()

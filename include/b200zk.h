@@ -251,6 +251,18 @@ int b200zk_lookup_product_dev(const void* const* d_compressed_input, const void*
                               uint32_t count, uint32_t k, const uint64_t beta[4], const uint64_t gamma[4],
                               uint32_t blinding_factors, const uint64_t* blinds_or_null, void* d_z, void* stream);
 
+/* halo2_proofs/src/plonk/lookup/prover.rs `permute_expression_pair` for `count` lookups: over the
+ * usable rows m = 2^k - (blinding_factors + 1), permuted_input = the input expression sorted by
+ * Fr's Ord (canonical integers); permuted_table carries each value at the row where it first
+ * appears in permuted_input, and the table's remaining values, ascending, at the rows of repeated
+ * inputs from the last such row backwards.  The last blinding_factors + 1 rows come from `blinds`
+ * (host; per lookup the input's scalars then the table's, count x 2 x (blinding_factors + 1) x 4
+ * limbs; zeros when null).  Column c of every array is at + c * stride elements.  Fails with
+ * "ConstraintSystemFailure" in the message when an input value does not occur in the table. */
+int b200zk_permute_expression_pair_dev(const void* d_input, const void* d_table, size_t stride, uint32_t count, uint32_t k,
+                                       uint32_t blinding_factors, const uint64_t* blinds_or_null, void* d_permuted_input,
+                                       void* d_permuted_table, size_t out_stride, void* stream);
+
 /* halo2_proofs/src/arithmetic.rs `eval_polynomial(poly, point)` for `count` polynomials of n
  * coefficients (polynomial c at d_polys + c * stride), each at its own point (host, count x 4
  * limbs); results to host memory `out` (count x 4 limbs). */

@@ -11,6 +11,7 @@ implementation (tests/test_prover_steps_oracle.py).
   * ``halo2_proofs/src/arithmetic.rs``  eval_polynomial, kate_division  eval_polynomial, kate_division
   * ``halo2_proofs/src/plonk/permutation/prover.rs``  Argument::commit  permutation_products
   * ``halo2_proofs/src/plonk/lookup/prover.rs``  Permuted::commit_product  lookup_product
+  * ``halo2_proofs/src/plonk/lookup/prover.rs``  permute_expression_pair   permute_expression_pair
 """
 from __future__ import annotations
 
@@ -100,3 +101,34 @@ def lookup_product(compressed_input, compressed_table, permuted_input, permuted_
             state = state * prod[i] % R
             tail.append(state)
     return z + tail
+
+
+def permute_expression_pair(input_expression, table_expression, blinding_factors, blinds=None):
+    """lookup/prover.rs permute_expression_pair, statement by statement: sort the usable rows of
+    the input (Fr's Ord = canonical integer order), count the table's values in an ordered map,
+    give every first occurrence of an input value its own value in the table column (taking one
+    instance out of the map; a missing value is ConstraintSystemFailure), then pop the repeated
+    rows from the END while walking the leftover table values in ascending order."""
+    n = len(input_expression)
+    usable = n - (blinding_factors + 1)
+    permuted_input = sorted(v % R for v in input_expression[:usable])
+    leftover = {}
+    for v in table_expression[:usable]:
+        leftover[v % R] = leftover.get(v % R, 0) + 1
+    permuted_table = [0] * usable
+    repeated_rows = []
+    for row, v in enumerate(permuted_input):
+        if row == 0 or v != permuted_input[row - 1]:
+            permuted_table[row] = v
+            if leftover.get(v, 0) <= 0:
+                raise ValueError("ConstraintSystemFailure")
+            leftover[v] -= 1
+        else:
+            repeated_rows.append(row)
+    for v in sorted(leftover):
+        for _ in range(leftover[v]):
+            permuted_table[repeated_rows.pop()] = v
+    assert not repeated_rows
+    tail_in = [b % R for b in blinds[0]] if blinds is not None else [0] * (blinding_factors + 1)
+    tail_tb = [b % R for b in blinds[1]] if blinds is not None else [0] * (blinding_factors + 1)
+    return permuted_input + tail_in, permuted_table + tail_tb

@@ -109,3 +109,39 @@ def test_lookup_products(zk, k, count, bf):
     got = zk.lookup_products(cols[0], cols[1], cols[2], cols[3], k, beta, gamma, bf)
     want = ps.lookup_product(I(cols[0][0]), I(cols[1][0]), I(cols[2][0]), I(cols[3][0]), beta, gamma, bf)
     assert I(got[0]) == want
+
+
+@pytest.mark.parametrize("k,count,bf,distinct", [(4, 1, 3, 5), (8, 3, 5, 40), (11, 2, 5, 4096), (12, 2, 5, 300), (13, 1, 5, 1 << 12)])
+def test_permute_expression_pairs(zk, k, count, bf, distinct):
+    """Random lookups whose table covers every input value, small and large value sets (runs of
+    repeated inputs, tables with duplicates), sizes on both sides of the 1024-key sort tile."""
+    n = 1 << k
+    usable = n - bf - 1
+    rnd = random.Random(k * 31 + count)
+    ins, tbs, blinds = [], [], []
+    for c in range(count):
+        vals = [rnd.randrange(R) for _ in range(min(distinct, usable))]
+        if c % 2:
+            vals = [v % 4096 for v in vals]                     # small witnesses: keys differ only in the low limb
+        tab = vals + [rnd.choice(vals) for _ in range(usable - len(vals))]
+        rnd.shuffle(tab)
+        inp = [rnd.choice(vals) for _ in range(usable)]
+        pad = [rnd.randrange(R) for _ in range(bf + 1)]         # ignored rows
+        ins.append(inp + pad); tbs.append(tab + pad)
+        blinds.append(([rnd.randrange(R) for _ in range(bf + 1)], [rnd.randrange(R) for _ in range(bf + 1)]))
+    got_in, got_tb = zk.permute_expression_pairs(np.stack([F(x) for x in ins]), np.stack([F(x) for x in tbs]), k, bf,
+                                                 np.stack([np.stack([F(b[0]), F(b[1])]) for b in blinds]))
+    for c in range(count):
+        want_in, want_tb = ps.permute_expression_pair(ins[c], tbs[c], bf, blinds[c])
+        assert I(got_in[c]) == want_in, f"permuted input {c}"
+        assert I(got_tb[c]) == want_tb, f"permuted table {c}"
+
+
+def test_permute_expression_pair_missing_value_is_an_error(zk):
+    k, bf = 6, 5
+    n = 1 << k
+    tab = list(range(1, n + 1))
+    inp = [1] * n
+    inp[3] = 10 ** 30                                           # not in the table
+    with pytest.raises(zk.B200zkError, match="ConstraintSystemFailure"):
+        zk.permute_expression_pairs(F(inp)[None], F(tab)[None], k, bf)

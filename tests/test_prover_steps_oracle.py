@@ -85,3 +85,25 @@ def test_lookup_product_closes_for_a_permuted_pair():
     beta, gamma = rnd.randrange(R), rnd.randrange(R)
     z = ps.lookup_product(a, s, a2, s2, beta, gamma, bf, blinds=[7, 8, 9])
     assert z[0] == 1 and z[usable] == 1 and z[-3:] == [7, 8, 9] and len(z) == n
+
+
+def test_permute_expression_pair_satisfies_the_lookup_constraints():
+    """The defining properties of the permuted pair (what the lookup argument's constraints
+    check): same multisets as the originals, and every row has a' == s' or a' == a'[row - 1],
+    with a'[0] == s'[0]."""
+    import pytest
+    rnd = random.Random(8)
+    n, bf = 64, 5
+    usable = n - bf - 1
+    table = [rnd.randrange(R) for _ in range(12)] + [3, 3, 7]
+    tab = [rnd.choice(table) for _ in range(usable)]
+    tab[:len(table)] = table                                   # every table value present at least once
+    inp = [rnd.choice(table) for _ in range(usable)]
+    pad = [0] * (bf + 1)
+    a, s = ps.permute_expression_pair(inp + pad, tab + pad, bf, blinds=([1] * (bf + 1), [2] * (bf + 1)))
+    assert sorted(a[:usable]) == sorted(inp) and sorted(s[:usable]) == sorted(tab)
+    assert a[usable:] == [1] * (bf + 1) and s[usable:] == [2] * (bf + 1)
+    assert a[0] == s[0]
+    assert all(a[i] == s[i] or a[i] == a[i - 1] for i in range(1, usable))
+    with pytest.raises(ValueError, match="ConstraintSystemFailure"):
+        ps.permute_expression_pair([R - 5] + inp[1:] + pad, tab + pad, bf)
