@@ -40,6 +40,7 @@ from .prover_steps import (  # noqa: F401,E402
     eval_polynomial,
     eval_polynomial_many,
     kate_division,
+    linear_combination,
     lookup_products,
     permutation_products,
     permute_expression_pairs,

@@ -87,6 +87,7 @@ def load() -> C.CDLL:
         "b200zk_permutation_product_dev": ([vp, vp, u32, u32, u32, vp, vp, vp, vp, u32, vp, vp, vp], C.c_int),
         "b200zk_lookup_product_dev": ([vp, vp, vp, vp, u32, u32, vp, vp, u32, vp, vp, vp], C.c_int),
         "b200zk_permute_expression_pair_dev": ([vp, vp, sz, u32, u32, u32, vp, vp, vp, sz, vp], C.c_int),
+        "b200zk_linear_combination_dev": ([vp, vp, u32, sz, vp, vp], C.c_int),
         "b200zk_eval_polynomial_dev": ([vp, sz, sz, sz, vp, vp, vp], C.c_int),
         "b200zk_kate_division_dev": ([vp, sz, vp, vp, vp], C.c_int),
         "b200zk_g1_to_bytes": ([vp, sz, vp], C.c_int),

@@ -241,6 +241,30 @@ class ParamsKZG:
         """`ParamsKZG::commit_lagrange(&poly, _blind) -> G1`."""
         return self._msm(self._h_gl, poly)
 
+    # ---- poly/kzg/commitment.rs ParamsKZG::{write, read} (v2023_01_20 framing): k as u32 LE, then
+    # g[0..n) and g_lagrange[0..n) as `G1Affine::to_bytes` (32 bytes each), then g2 and s_g2 as
+    # `G2Affine::to_bytes` (64 bytes each).  The G2 points never touch the hot path: they are
+    # carried through as opaque bytes.  Compression and the n square roots of decompression run
+    # on the device (b200zk_g1_affine_to_bytes / b200zk_g1_affine_from_bytes).
+    @staticmethod
+    def write_bytes(g: np.ndarray, g_lagrange: np.ndarray, g2: bytes, s_g2: bytes) -> bytes:
+        n = g.shape[0]
+        assert n & (n - 1) == 0 and g_lagrange.shape == g.shape and len(g2) == 64 and len(s_g2) == 64
+        k = n.bit_length() - 1
+        return (k.to_bytes(4, "little") + g1_affine_to_bytes(g).tobytes() + g1_affine_to_bytes(g_lagrange).tobytes()
+                + bytes(g2) + bytes(s_g2))
+
+    @classmethod
+    def read_bytes(cls, data: bytes, precompute_windows: bool = True):
+        """Returns (ParamsKZG, g, g_lagrange, g2_bytes, s_g2_bytes)."""
+        k = int.from_bytes(data[:4], "little")
+        n = 1 << k
+        assert len(data) == 4 + 64 * n + 128, "truncated params"   # upstream: read_exact fails
+        body = np.frombuffer(data, dtype=np.uint8, count=64 * n, offset=4).reshape(2, n, 32)
+        g = g1_affine_from_bytes(body[0])
+        g_lagrange = g1_affine_from_bytes(body[1])
+        return cls(g, g_lagrange, precompute_windows), g, g_lagrange, data[4 + 64 * n: 68 + 64 * n], data[68 + 64 * n:]
+
     def close(self) -> None:
         for name in ("_h_g", "_h_gl"):
             h = getattr(self, name, 0)

@@ -134,3 +134,19 @@ def permute_expression_pairs(inputs: np.ndarray, tables: np.ndarray, k: int, bli
     finally:
         for c in (din, dtb, oin, otb):
             c.free()
+
+
+def linear_combination(polys, coeffs) -> np.ndarray:
+    """sum_j coeffs[j] * polys[j] (the `acc * y + poly` chains of the multi-open provers)."""
+    count = len(polys)
+    assert count == len(coeffs) and count >= 1
+    n = polys[0].shape[0]
+    dev = [DeviceColumn.from_host(p) for p in polys]
+    out = DeviceColumn(n)
+    cl = np.stack([_as_fr_scalar(c) for c in coeffs])
+    ptrs = _ptr_array(dev)
+    check(load().b200zk_linear_combination_dev(ptrs, _ptr(cl), count, n, C.c_void_p(out.ptr), None))
+    res = out.to_host()
+    for c in dev + [out]:
+        c.free()
+    return res

@@ -396,6 +396,19 @@ static __global__ void __launch_bounds__(PT) kate_tile_kernel(const Fr* __restri
     }
 }
 
+// -------------------------------------------------------------- linear combinations
+// out[i] = sum_j coeff[j] * poly_j[i]: the `acc * y + poly` / `poly * scalar` chains of the
+// multi-open provers (halo2_proofs/src/poly/kzg/multiopen/{shplonk,gwc}/prover.rs) collapsed
+// into one pass that reads every column once (HBM-bound: count x 32 B per output element).
+static __global__ void linear_combination_kernel(const Fr* const* __restrict__ polys, const Fr* __restrict__ coeffs,
+                                                 uint32_t count, size_t n, Fr* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr acc = Fr::zero();
+    for (uint32_t j = 0; j < count; ++j) acc = acc + ldg_fr(coeffs + j) * ldg_fr(polys[j] + i);
+    st_fr(out + i, acc.canon());
+}
+
 }  // namespace zk
 
 using namespace zk;
@@ -630,6 +643,30 @@ int b200zk_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], voi
         kate_tile_kernel<<<ntiles, PT, 0, s>>>((const Fr*)d_a, n, bb, carry_in, (Fr*)d_q);
         ZK_LAUNCH_CHECK();
         ZK_CUDA(cudaStreamSynchronize(s));        // `bb` staging
+    });
+}
+
+int b200zk_linear_combination_dev(const void* const* d_polys, const uint64_t* coeffs, uint32_t count, size_t n,
+                                  void* d_out, void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_out || n == 0, "null argument");
+        ZK_REQUIRE(count == 0 || (d_polys && coeffs), "null argument");
+        if (n == 0) return;
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = pick_stream(stream);
+        const size_t ptr_bytes = (size_t)count * sizeof(void*);
+        const size_t o_c = (ptr_bytes + 255) / 256 * 256;
+        char* small = (char*)c.poly_small.get(o_c + (size_t)count * sizeof(Fr) + 256);
+        for (uint32_t j = 0; j < count; ++j) ZK_REQUIRE(d_polys[j], "null column pointer");
+        if (count) {
+            ZK_CUDA(cudaMemcpyAsync(small, d_polys, ptr_bytes, cudaMemcpyHostToDevice, s));
+            ZK_CUDA(cudaMemcpyAsync(small + o_c, coeffs, (size_t)count * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        }
+        linear_combination_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const Fr* const*)small, (const Fr*)(small + o_c),
+                                                                             count, n, (Fr*)d_out);
+        ZK_LAUNCH_CHECK();
+        ZK_CUDA(cudaStreamSynchronize(s));   // the host arrays may go away after return
     });
 }
 

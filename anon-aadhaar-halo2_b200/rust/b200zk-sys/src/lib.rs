@@ -67,6 +67,7 @@ extern "C" {
     pub fn b200zk_permutation_product_dev(d_values: *const *const c_void, d_sigma: *const *const c_void, n_cols: u32, chunk_len: u32, k: u32, beta: *const u64, gamma: *const u64, omega: *const u64, delta: *const u64, blinding_factors: u32, blinds_or_null: *const u64, d_z: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn b200zk_lookup_product_dev(d_compressed_input: *const *const c_void, d_compressed_table: *const *const c_void, d_permuted_input: *const *const c_void, d_permuted_table: *const *const c_void, count: u32, k: u32, beta: *const u64, gamma: *const u64, blinding_factors: u32, blinds_or_null: *const u64, d_z: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn b200zk_permute_expression_pair_dev(d_input: *const c_void, d_table: *const c_void, stride: usize, count: u32, k: u32, blinding_factors: u32, blinds_or_null: *const u64, d_permuted_input: *mut c_void, d_permuted_table: *mut c_void, out_stride: usize, stream: *mut c_void) -> c_int;
+    pub fn b200zk_linear_combination_dev(d_polys: *const *const c_void, coeffs: *const u64, count: u32, n: usize, d_out: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn b200zk_eval_polynomial_dev(d_polys: *const c_void, stride: usize, count: usize, n: usize, points: *const u64, out: *mut u64, stream: *mut c_void) -> c_int;
     pub fn b200zk_kate_division_dev(d_a: *const c_void, n: usize, b: *const u64, d_q: *mut c_void, stream: *mut c_void) -> c_int;
 

@@ -273,6 +273,13 @@ int b200zk_eval_polynomial_dev(const void* d_polys, size_t stride, size_t count,
  * (X - b), n - 1 coefficients to d_q (the remainder a(b) is dropped, as upstream). */
 int b200zk_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q, void* stream);
 
+/* out[i] = sum_j coeffs[j] * polys[j][i] over `count` device columns of n elements (coeffs: host,
+ * count x 4 limbs): the `acc * y + poly` accumulations of the multi-open provers
+ * (halo2_proofs/src/poly/kzg/multiopen/{shplonk,gwc}/prover.rs) in one pass.  d_out may be one
+ * of the inputs. */
+int b200zk_linear_combination_dev(const void* const* d_polys, const uint64_t* coeffs, uint32_t count, size_t n,
+                                  void* d_out, void* stream);
+
 /* ---- wire formats of G1 points (SURVEY.md section 8 f, rank 3) ---------------------------- */
 /* halo2curves 0.3.1 src/derive/curve.rs `G1Affine::to_bytes` applied to `count` points: 32 bytes
  * each, x little-endian canonical with the parity of y in bit 7 of byte 31, identity = zeros.

@@ -56,3 +56,22 @@ def test_from_bytes_rejects_bad_points(zk):
         zk.g1_affine_from_bytes(np.stack([good, not_canonical]))
     with pytest.raises(zk.B200zkError, match="point 2.*curve"):
         zk.g1_affine_from_bytes(np.stack([good, good, off_curve]))
+
+
+def test_params_kzg_write_read_round_trip(zk):
+    """ParamsKZG::write / read framing around the device point codecs: the re-read tables are
+    identical and commit to the same point."""
+    n = 1 << 9
+    g, gl = co.gen_points(0x9A1, n), co.gen_points(0x9A2, n)
+    g2, s_g2 = bytes(range(64)), bytes(range(64, 128))
+    blob = zk.ParamsKZG.write_bytes(g, gl, g2, s_g2)
+    assert len(blob) == 4 + 64 * n + 128 and blob[:4] == (9).to_bytes(4, "little")
+    assert blob[4:36] == bn.g1_to_bytes(bn.g1_affine_array_to_points(g[:1])[0])
+    params, g_back, gl_back, g2_back, s_back = zk.ParamsKZG.read_bytes(blob)
+    assert np.array_equal(g_back, g) and np.array_equal(gl_back, gl) and g2_back == g2 and s_back == s_g2
+    poly = co.gen_scalars(0x9A3, n)
+    want = bn.g1_jacobian_limbs_to_affine(co.best_multiexp(poly, gl))
+    assert bn.g1_jacobian_limbs_to_affine(params.commit_lagrange(poly)) == want
+    params.close()
+    with pytest.raises(AssertionError, match="truncated"):
+        zk.ParamsKZG.read_bytes(blob[:-1])

@@ -145,3 +145,14 @@ def test_permute_expression_pair_missing_value_is_an_error(zk):
     inp[3] = 10 ** 30                                           # not in the table
     with pytest.raises(zk.B200zkError, match="ConstraintSystemFailure"):
         zk.permute_expression_pairs(F(inp)[None], F(tab)[None], k, bf)
+
+
+def test_linear_combination(zk):
+    rnd = random.Random(12)
+    n, count = 5000, 7
+    polys = [co.gen_scalars(0x11C + j, n) for j in range(count)]
+    coeffs = [rnd.randrange(R) for _ in range(count)]
+    coeffs[2], coeffs[3] = 0, 1
+    got = I(zk.linear_combination(polys, coeffs))
+    cols = [I(p) for p in polys]
+    assert got == [sum(c * col[i] for c, col in zip(coeffs, cols)) % R for i in range(n)]
