@@ -12,7 +12,9 @@ b200zk.check(lib.b200zk_gen_points_dev(C.c_void_p(db.data_ptr()), n, 1, 0))
 hb = db.cpu().numpy().view(np.uint64).reshape(n, 8)
 h = C.c_uint64(0); b200zk.check(lib.b200zk_bases_register(_ptr(hb), n, C.byref(h)))
 b200zk.check(lib.b200zk_msm_profile(1))
-for cnt in (3, 48, 82, 112, 242):
+import os
+if os.environ.get("SEGLEN"): b200zk.check(lib.b200zk_msm_tune(128, int(os.environ["SEGLEN"]), 0))
+for cnt in (3, 112, 242):
     ds = torch.empty(cnt * n * 4, dtype=torch.int64, device="cuda")
     b200zk.check(lib.b200zk_gen_scalars_dev(C.c_void_p(ds.data_ptr()), cnt * n, 5, 0))
     dout = torch.zeros(cnt * 12, dtype=torch.int64, device="cuda")
