@@ -83,8 +83,40 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []          # (t, sm_mhz, max_mhz, watts, reasons bitmask) from NVML
+        self._stop = threading.Event()
+
+    # NVML clocks-event-reason bits (nvml.h): sw power cap 0x4, hw slowdown 0x8, sw thermal 0x20, hw thermal 0x40
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        try:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.perf_counter(), float(sm), float(mx), pw, int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
@@ -99,6 +131,18 @@ class ClockSampler:
             self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self, t_begin: float = 0.0, t_end: float = 1e300) -> dict:
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            inside = [x for x in self.samples if t_begin <= x[0] <= t_end]
+            window = "timed region"
+            if not inside:
+                inside, window = list(self.samples), "warm-up + timed region"
+            reasons = sorted(nm for nm, bit in self.REASON_BITS.items() if any(x[4] & bit for x in inside))
+            return {"sm_mhz": statistics.median(x[1] for x in inside) if inside else None,
+                    "sm_max_mhz": max((x[2] for x in inside), default=None),
+                    "power_w_max": max((x[3] for x in inside), default=None), "samples": len(inside),
+                    "window": window, "source": "NVML, 5 ms period", "reasons": reasons}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -127,7 +171,7 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window,
-                "reasons": sorted(reasons)}
+                "source": "nvidia-smi -lms 100", "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------- CPU arm
