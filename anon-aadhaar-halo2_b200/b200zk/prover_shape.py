@@ -236,6 +236,154 @@ class ProverHotPath:
         t["total"] = sum(t.values())
         return t
 
+    # ------------------------------------------------------------ one proof over several GPUs
+    # SURVEY.md section 8 e: commitments and iNTTs are dealt by column, the coefficient columns are
+    # all-gathered (the one bulk exchange), every rank extends and evaluates only "its" cosets of the
+    # extended domain (b200zk_coeff_to_coset_dev: 1/P of a coeff_to_extended per coset), the evaluated
+    # cosets are gathered on rank 0, which interleaves them and finishes h(X).
+    class _CudaView:
+        """Zero-copy torch view of library-owned device memory (for the NCCL collectives)."""
+
+        def __init__(self, ptr: int, n_int64: int):
+            self.__cuda_array_interface__ = {"shape": (n_int64,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+    def _torch_view(self, torch, col: DeviceColumn, offset_elems: int, n_elems: int):
+        return torch.as_tensor(self._CudaView(col.ptr + offset_elems * 32, n_elems * 4), device="cuda")
+
+    def prepare_sharded(self, world: int, rank: int) -> None:
+        from .sharding import shard_range
+        lib, s, d, n, N = self.lib, self.shape, self.domain, self.n, self.N
+        self.world, self.rank = world, rank
+        self.parts = 1 << (d.extended_k - d.k)
+        self.my_cosets = list(range(rank, self.parts, world))
+        self.cosets_per_rank = -(-self.parts // world)
+        self.col_b, self.col_e = shard_range(self.n_lag, rank, world)
+        self.maxc = -(-self.n_lag // world)
+        # padded copy of the Lagrange columns so every rank's block has maxc columns
+        self.lag_pad = DeviceColumn((self.n_lag + self.maxc) * n)
+        self.coef_all = DeviceColumn(world * self.maxc * n)
+        self.cos = DeviceColumn((world * self.maxc + s.instance) * n)
+        self.cos_views = [DeviceColumn.view(self.cos, i * n, n) for i in range(world * self.maxc + s.instance)]
+        self.h_mine = DeviceColumn(self.cosets_per_rank * n)
+        self.h_all = DeviceColumn(world * self.cosets_per_rank * n)
+        n_pk = s.fixed + s.permutation_columns + 3
+        self.pk_coset = {}
+        for q in self.my_cosets:
+            c = DeviceColumn(n_pk * n)
+            check(lib.b200zk_extended_coset_slice_dev(C.c_void_p(self.pk_cols.ptr), N, C.c_void_p(c.ptr), n, n_pk, d.k,
+                                                      d.extended_k, q, None))
+            self.pk_coset[q] = (c, [DeviceColumn.view(c, i * n, n) for i in range(n_pk)])
+        # global column index -> position in the gathered buffer
+        self.col_pos = []
+        for r in range(world):
+            b, e = shard_range(self.n_lag, r, world)
+            self.col_pos += [r * self.maxc + (cidx - b) for cidx in range(b, e)]
+        from .api import FR_MODULUS
+        self.coset_gen = [fr_limbs(FR_ZETA * pow(d.extended_omega_int, q, FR_MODULUS) % FR_MODULUS) for q in range(self.parts)]
+
+    def run_sharded(self, torch, dist=None) -> dict:
+        """The same proof as run(), spread over `world` ranks (prepare_sharded first).  world = 1
+        exercises the whole coset path on one GPU.  `torch` supplies the NCCL collectives and the
+        device copies around library-owned memory."""
+        lib, s, d, n, N = self.lib, self.shape, self.domain, self.n, self.N
+        world, rank = self.world, self.rank
+        t, marks = {}, [time.perf_counter()]
+
+        def mark(name):
+            self.sync()
+            marks.append(time.perf_counter())
+            t[name] = 1e3 * (marks[-1] - marks[-2])
+
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.lag_pad.ptr), self.n_lag * n, self.seed + 2, 0))
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.instance_coeff.ptr), self.instance_coeff.n, self.seed + 3, 0))
+        self.sync()
+        if world > 1:
+            dist.barrier()
+        marks[0] = time.perf_counter()
+        b, e = self.col_b, self.col_e
+        mine = self.lag_pad.ptr + b * n * 32
+        if e > b:
+            self._commit(mine, e - b, b)
+            check(lib.b200zk_ntt_dev(C.c_void_p(mine), n, e - b, d.k, _ptr(d.omega_inv), _ptr(d.ifft_divisor), None))
+        mark("commit_and_lagrange_to_coeff_own_columns")
+        if world > 1:
+            dist.all_gather_into_tensor(self._torch_view(torch, self.coef_all, 0, world * self.maxc * n),
+                                        self._torch_view(torch, self.lag_pad, b * n, self.maxc * n))
+            pts_all = torch.zeros(world * self.maxc * 12, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(pts_all, self._torch_view(torch, self.points, b * 3, self.maxc * 3))
+        else:
+            self._torch_view(torch, self.coef_all, 0, self.maxc * n).copy_(self._torch_view(torch, self.lag_pad, 0, self.maxc * n))
+        mark("all_gather_coefficient_columns")
+        env_scal = self.scalars
+        zeta_delta = fr_limbs(FR_DELTA)
+        for slot, q in enumerate(self.my_cosets):
+            g = self.coset_gen[q]
+            ncols = world * self.maxc
+            check(lib.b200zk_coeff_to_coset_dev(C.c_void_p(self.coef_all.ptr), n, C.c_void_p(self.cos.ptr), n, ncols, d.k,
+                                                _ptr(d.omega), _ptr(g), None))
+            check(lib.b200zk_coeff_to_coset_dev(C.c_void_p(self.instance_coeff.ptr), n,
+                                                C.c_void_p(self.cos.ptr + ncols * n * 32), n, s.instance, d.k,
+                                                _ptr(d.omega), _ptr(g), None))
+            col = lambda cidx: self.cos_views[self.col_pos[cidx]]
+            advice = [col(i) for i in range(s.advice)]
+            instance = self.cos_views[ncols: ncols + s.instance]
+            pkc, pkv = self.pk_coset[q]
+            fixed, sigma = pkv[: s.fixed], pkv[s.fixed: s.fixed + s.permutation_columns]
+            l0, l_last, l_active = pkv[-3:]
+            keep = [_handles(fixed), _handles(advice), _handles(instance), np.zeros((1, 4), np.uint64)]
+            env = EnvC()
+            env.fixed, env.n_fixed = keep[0].ctypes.data, len(fixed)
+            env.advice, env.n_advice = keep[1].ctypes.data, len(advice)
+            env.instance, env.n_instance = keep[2].ctypes.data, len(instance)
+            env.challenges, env.n_challenges = keep[3].ctypes.data, 0
+            for name in ("beta", "gamma", "theta", "y"):
+                getattr(env, name)[:] = [int(x) for x in env_scal[name]]
+            env.k, env.ext_k = d.k, d.k
+            env.range_begin, env.range_len = 0, 0
+            values = DeviceColumn.view(self.h_mine, slot * n, n)
+            gg = self.gates.as_c()
+            check(lib.b200zk_quotient_graph(C.byref(gg), C.byref(env), 0, values.handle))
+            lk0, pp0 = s.advice, s.advice + 2 * s.lookups
+            lp0 = pp0 + s.permutation_sets
+            products = [col(pp0 + i) for i in range(s.permutation_sets)]
+            sig, ph = _handles(sigma), _handles(products)
+            check(lib.b200zk_quotient_permutation(
+                C.byref(env), values.handle, _ptr32(self.perm_kind), _ptr32(self.perm_index), _ptr(sig),
+                len(self.perm_kind), _ptr(ph), len(products), s.degree - 2, s.blinding_factors, l0.handle,
+                l_last.handle, l_active.handle, _ptr(d.omega), _ptr(g), _ptr(zeta_delta)))
+            for j in range(s.lookups):
+                lg = self.lookup_graphs[j].as_c()
+                check(lib.b200zk_quotient_graph(C.byref(lg), C.byref(env), 0, self.table.handle))
+                check(lib.b200zk_quotient_lookup(C.byref(env), values.handle, self.table.handle, col(lp0 + j).handle,
+                                                 col(lk0 + 2 * j).handle, col(lk0 + 2 * j + 1).handle, l0.handle,
+                                                 l_last.handle, l_active.handle))
+            values.free()
+        mark("coset_ntt_and_quotient_own_cosets")
+        if world > 1:
+            dist.all_gather_into_tensor(self._torch_view(torch, self.h_all, 0, world * self.cosets_per_rank * n),
+                                        self._torch_view(torch, self.h_mine, 0, self.cosets_per_rank * n))
+        mark("gather_h_cosets")
+        if rank == 0:
+            for q in range(self.parts):
+                owner, slot = q % world, q // world
+                srcbuf = self.h_all if world > 1 else self.h_mine
+                off = (owner * self.cosets_per_rank + slot) * n if world > 1 else slot * n
+                check(lib.b200zk_extended_coset_interleave_dev(C.c_void_p(srcbuf.ptr + off * 32), C.c_void_p(self.values.ptr),
+                                                               d.k, d.extended_k, q, None))
+            t_ev = DeviceColumn.from_host(d.t_evaluations)
+            keep_n = n * (s.degree - 1)
+            check(lib.b200zk_extended_to_coeff_dev(C.c_void_p(self.values.ptr), d.extended_k, _ptr(d.extended_omega_inv),
+                                                   _ptr(d.extended_ifft_divisor), _ptr(d.g_coset), C.c_void_p(t_ev.ptr),
+                                                   d.t_evaluations.shape[0], C.c_void_p(self.h_coeff.ptr), keep_n, None))
+            self._commit(self.h_coeff.ptr, s.degree - 1, self.n_lag + 1)
+            self.sync()
+            t_ev.free()
+        mark("finish_h_on_rank0")
+        if world > 1:
+            dist.barrier()
+        t["total"] = 1e3 * (time.perf_counter() - marks[0])
+        return t
+
     def counts(self) -> dict:
         s = self.shape
         return {"commit_lagrange": s.lagrange_columns, "commit": s.degree - 1, "lagrange_to_coeff": s.lagrange_columns,

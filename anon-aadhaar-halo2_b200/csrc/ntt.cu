@@ -289,6 +289,34 @@ static __global__ void __launch_bounds__(256) ntt4_twiddle_scatter_kernel(const 
     }
 }
 
+
+// ------------------------------------------------- cosets of the extended domain (multi-GPU h(X))
+// The extended domain {zeta * w_ext^e} splits into P = 2^(ext_k - k) cosets of the base domain:
+// e = P j + q  <->  point (zeta w_ext^q) * w^j.  Coset q of a polynomial is an n-point transform of
+// its coefficients scaled by (zeta w_ext^q)^i, rotations by w stay inside a coset, so one GPU can
+// produce and consume "its" cosets of every column without ever holding an extended column.
+static __global__ void fr_scale_pow_kernel(const Fr* __restrict__ in, size_t in_stride, Fr* __restrict__ out,
+                                           size_t out_stride, uint32_t n, const Fr* __restrict__ pow_table) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (i >= n) return;
+    st_fr(out + (size_t)c * out_stride + i, ldg_fr(in + (size_t)c * in_stride + i) * ldg_fr(pow_table + i));
+}
+
+// out[c][j] = ext[c][(j << shift) + q]   (gather one coset out of extended columns)
+static __global__ void coset_slice_kernel(const Fr* __restrict__ ext, size_t ext_stride, Fr* __restrict__ out,
+                                          size_t out_stride, uint32_t n, uint32_t shift, uint32_t q) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (j >= n) return;
+    st_fr(out + (size_t)c * out_stride + j, ldg_fr(ext + (size_t)c * ext_stride + (((size_t)j << shift) + q)));
+}
+// ext[(j << shift) + q] = in[j]   (scatter a coset back into an extended column)
+static __global__ void coset_interleave_kernel(const Fr* __restrict__ in, Fr* __restrict__ ext, uint32_t n, uint32_t shift,
+                                               uint32_t q) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    st_fr(ext + (((size_t)j << shift) + q), ldg_fr(in + j));
+}
+
 }  // namespace zk
 
 using namespace zk;
@@ -506,6 +534,61 @@ int b200zk_ntt4_gather_rows_dev(const void* d_recv, void* d_out, uint32_t log_n,
         for (uint32_t r = 0; r < world; ++r)
             ZK_CUDA(cudaMemcpy2DAsync((Fr*)d_out + r * m, n2 * sizeof(Fr), (const Fr*)d_recv + r * rows * m,
                                       m * sizeof(Fr), m * sizeof(Fr), rows, cudaMemcpyDeviceToDevice, s));
+    });
+}
+
+int b200zk_coeff_to_coset_dev(const void* d_in, size_t in_stride, void* d_out, size_t out_stride, size_t count,
+                              uint32_t k, const uint64_t omega[4], const uint64_t coset_generator[4], void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_in && d_out && omega && coset_generator, "null argument");
+        ZK_REQUIRE(k >= 1 && k <= 28, "k out of range");
+        ensure_init();
+        Context& c = ctx();
+        const uint64_t n = (uint64_t)1 << k;
+        check_batch(in_stride, count, n);
+        check_batch(out_stride, count, n);
+        if (count == 0) return;
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        // powers of the coset generator, one table per call (n entries, ~30 products each)
+        Fr* pw = (Fr*)c.ntt_aux.get(n * sizeof(Fr));
+        fr_pow_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(fr_from_limbs(coset_generator), 1, (uint32_t)n, pw);
+        ZK_LAUNCH_CHECK();
+        fr_scale_pow_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)count), 256, 0, s>>>(
+            (const Fr*)d_in, in_stride, (Fr*)d_out, out_stride, (uint32_t)n, pw);
+        ZK_LAUNCH_CHECK();
+        Fr* tmp = (Fr*)c.ntt_tmp.get(count * n * sizeof(Fr));
+        ntt_run(c, (Fr*)d_out, out_stride, (Fr*)d_out, out_stride, tmp, count, k, fr_from_limbs(omega), NttMods(), s);
+    });
+}
+
+int b200zk_extended_coset_slice_dev(const void* d_ext, size_t ext_stride, void* d_out, size_t out_stride, size_t count,
+                                    uint32_t k, uint32_t ext_k, uint32_t coset, void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_ext && d_out && d_ext != d_out, "bad buffers");
+        ZK_REQUIRE(k >= 1 && ext_k >= k && ext_k <= 28 && coset < (1u << (ext_k - k)), "bad coset");
+        ZK_REQUIRE(count <= 65535, "batch count exceeds 65535");
+        ensure_init();
+        Context& c = ctx();
+        if (count == 0) return;
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        const uint32_t n = 1u << k;
+        coset_slice_kernel<<<dim3((n + 255) / 256, (unsigned)count), 256, 0, s>>>((const Fr*)d_ext, ext_stride, (Fr*)d_out,
+                                                                                   out_stride, n, ext_k - k, coset);
+        ZK_LAUNCH_CHECK();
+    });
+}
+
+int b200zk_extended_coset_interleave_dev(const void* d_coset, void* d_ext, uint32_t k, uint32_t ext_k, uint32_t coset,
+                                         void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_coset && d_ext && d_coset != d_ext, "bad buffers");
+        ZK_REQUIRE(k >= 1 && ext_k >= k && ext_k <= 28 && coset < (1u << (ext_k - k)), "bad coset");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        const uint32_t n = 1u << k;
+        coset_interleave_kernel<<<(n + 255) / 256, 256, 0, s>>>((const Fr*)d_coset, (Fr*)d_ext, n, ext_k - k, coset);
+        ZK_LAUNCH_CHECK();
     });
 }
 

@@ -85,6 +85,22 @@ int b200zk_extended_to_coeff_dev(const void* d_a, uint32_t ext_k, const uint64_t
                                  const void* d_t_evaluations_or_null, uint32_t t_len, void* d_out, size_t keep,
                                  void* stream);
 
+/* Cosets of the extended domain, for evaluating h(X) on several GPUs (SURVEY.md section 8 e).  The
+ * extended domain {zeta * w_ext^e} is the union of P = 2^(ext_k - k) cosets of the base domain:
+ * e = P j + q is the point (zeta w_ext^q) w^j, and a rotation by w stays inside a coset.  So the
+ * rank that owns coset q needs, per column, one 2^k-point transform of the coefficients scaled by
+ * g^i with g = zeta * w_ext^q (`b200zk_coeff_to_coset_dev`), the matching slices of the proving
+ * key's extended columns (`b200zk_extended_coset_slice_dev`), and runs the quotient kernels with
+ * k = ext_k = k, extended_omega = w, zeta = g.  `b200zk_extended_coset_interleave_dev` puts an
+ * evaluated coset back at e = P j + q of the extended numerator before extended_to_coeff.
+ * Equivalent to coeff_to_extended followed by taking every P-th element, at 1/P of the work. */
+int b200zk_coeff_to_coset_dev(const void* d_in, size_t in_stride, void* d_out, size_t out_stride, size_t count,
+                              uint32_t k, const uint64_t omega[4], const uint64_t coset_generator[4], void* stream);
+int b200zk_extended_coset_slice_dev(const void* d_ext, size_t ext_stride, void* d_out, size_t out_stride, size_t count,
+                                    uint32_t k, uint32_t ext_k, uint32_t coset, void* stream);
+int b200zk_extended_coset_interleave_dev(const void* d_coset, void* d_ext, uint32_t k, uint32_t ext_k, uint32_t coset,
+                                         void* stream);
+
 /* One best_fft of 2^log_n elements sharded over `world` (1, 2, 4 or 8) GPUs, one process per
  * GPU (SURVEY.md section 8 e).  n = n1 * n2 with n1 = 2^log_n1; rank r holds the columns
  * j2 in [r m, (r + 1) m), m = n2 / world, as d_in[j2 - r m][j1] = a[j1 * n2 + j2].  The caller
