@@ -109,7 +109,76 @@ def main() -> None:
     add_case("small_scalars", [i % 5 for i in range(64)], pts[:64])
     msm["names"] = np.array(names)
     np.savez_compressed(OUT / "msm_kat.npz", **msm)
+    prover_steps()
     print("wrote", sorted(p.name for p in OUT.glob("*.npz")))
+
+
+def prover_steps() -> None:
+    """Known answers for the prover steps either side of the hot path (SURVEY.md section 8 f),
+    from the DEFINITIONS (modular inverses by pow(x, -1), polynomial identities, products of
+    fractions), not from oracle/prover_steps_cpu.py, which the tests then check against these."""
+    OUT.mkdir(parents=True, exist_ok=True)
+    rnd = random.Random(0xF1F2)
+    g = {}
+    R = bn.R
+    # batch_invert
+    a = [rnd.randrange(R) for _ in range(24)]
+    a[5] = 0
+    g["inv_in"] = bn.fr_array_from_canonical(a)
+    g["inv_out"] = bn.fr_array_from_canonical([pow(x, -1, R) if x else 0 for x in a])
+    # eval_polynomial / kate_division: q(X) (X - b) + a(b) == a(X)
+    poly = [rnd.randrange(R) for _ in range(37)]
+    x = rnd.randrange(R)
+    g["eval_poly"] = bn.fr_array_from_canonical(poly)
+    g["eval_point"] = bn.fr_array_from_canonical([x])[0]
+    g["eval_out"] = bn.fr_array_from_canonical([sum(c * pow(x, i, R) for i, c in enumerate(poly)) % R])[0]
+    b = rnd.randrange(R)
+    q = [0] * (len(poly) - 1)                    # schoolbook division by (X - b), from the top
+    rem = list(poly)
+    for i in range(len(poly) - 1, 0, -1):
+        q[i - 1] = rem[i]
+        rem[i - 1] = (rem[i - 1] + b * rem[i]) % R
+    g["kate_b"] = bn.fr_array_from_canonical([b])[0]
+    g["kate_out"] = bn.fr_array_from_canonical(q)
+    # permutation grand products by definition: z_s[i] = z_s[0] * prod_{r < i} num_s(r) / den_s(r)
+    k, n_cols, chunk, bf = 4, 5, 2, 3
+    n = 1 << k
+    omega = omega_for(k)
+    vals = [[rnd.randrange(R) for _ in range(n)] for _ in range(n_cols)]
+    sig = [[rnd.randrange(R) for _ in range(n)] for _ in range(n_cols)]
+    beta, gamma = rnd.randrange(R), rnd.randrange(R)
+    zs, first = [], 1
+    for lo in range(0, n_cols, chunk):
+        cols = range(lo, min(lo + chunk, n_cols))
+        z = [first]
+        for r in range(n - 1):
+            num = den = 1
+            for j in cols:
+                num = num * (vals[j][r] + pow(bn.FR_DELTA, j, R) * pow(omega, r, R) * beta + gamma) % R
+                den = den * (vals[j][r] + beta * sig[j][r] + gamma) % R
+            z.append(z[-1] * num * pow(den, -1, R) % R)
+        first = z[n - (bf + 1)]
+        zs.append(z)
+    g["perm_shape"] = np.array([k, n_cols, chunk, bf], dtype=np.int64)
+    g["perm_values"] = np.stack([bn.fr_array_from_canonical(v) for v in vals])
+    g["perm_sigma"] = np.stack([bn.fr_array_from_canonical(v) for v in sig])
+    g["perm_beta_gamma"] = bn.fr_array_from_canonical([beta, gamma])
+    g["perm_z"] = np.stack([bn.fr_array_from_canonical(z) for z in zs])
+    # lookup grand product by definition
+    ci, ct, pi, pt = ([rnd.randrange(R) for _ in range(n)] for _ in range(4))
+    z = [1]
+    for r in range(n - 1):
+        num = (ci[r] + beta) * (ct[r] + gamma) % R
+        den = (pi[r] + beta) * (pt[r] + gamma) % R
+        z.append(z[-1] * num * pow(den, -1, R) % R)
+    g["lookup_cols"] = np.stack([bn.fr_array_from_canonical(v) for v in (ci, ct, pi, pt)])
+    g["lookup_z"] = bn.fr_array_from_canonical(z)
+    # G1 wire formats: identity, G, -G, 2G (the public EIP-196 value), a random multiple
+    pts = [None, (1, 2), (1, bn.Q - 2), bn.g1_mul((1, 2), 2), bn.g1_mul((1, 2), rnd.randrange(R))]
+    g["enc_points"] = bn.g1_affine_array_from_points(pts)
+    g["enc_bytes"] = np.frombuffer(b"".join(bn.g1_to_bytes(p) for p in pts), dtype=np.uint8).reshape(len(pts), 32)
+    g["enc_evm"] = np.frombuffer(b"".join(bn.g1_to_evm_bytes(p) for p in pts), dtype=np.uint8).reshape(len(pts), 64)
+    np.savez_compressed(OUT / "prover_steps_kat.npz", **g)
 
 
 if __name__ == "__main__":

@@ -156,3 +156,31 @@ def test_linear_combination(zk):
     got = I(zk.linear_combination(polys, coeffs))
     cols = [I(p) for p in polys]
     assert got == [sum(c * col[i] for c, col in zip(coeffs, cols)) % R for i in range(n)]
+
+
+def test_device_matches_the_definition_golden(zk):
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "prover_steps_kat.npz")
+    one = lambda a: I(a[None, :])[0]
+    inv = g["inv_in"].copy()
+    zk.batch_invert(inv)
+    assert np.array_equal(inv, g["inv_out"])
+    assert np.array_equal(zk.eval_polynomial(g["eval_poly"], g["eval_point"]), g["eval_out"])
+    assert np.array_equal(zk.kate_division(g["eval_poly"], g["kate_b"]), g["kate_out"])
+    k, n_cols, chunk, bf = (int(x) for x in g["perm_shape"])
+    beta, gamma = g["perm_beta_gamma"]
+    got = zk.permutation_products(list(g["perm_values"]), list(g["perm_sigma"]), chunk, k, beta, gamma, bf)
+    assert np.array_equal(got, g["perm_z"])
+    ci, ct, pi, pt = g["lookup_cols"]
+    got = zk.lookup_products([ci], [ct], [pi], [pt], k, beta, gamma, bf)
+    assert np.array_equal(got[0], g["lookup_z"])
+    assert np.array_equal(zk.g1_affine_to_bytes(g["enc_points"]), g["enc_bytes"])
+    assert np.array_equal(zk.g1_affine_from_bytes(g["enc_bytes"]), g["enc_points"])
+    jac = np.zeros((g["enc_points"].shape[0], 12), dtype=np.uint64)
+    jac[:, :8] = g["enc_points"]
+    jac[1:, 8:] = bn.fr_array_from_canonical([0])[0]          # placeholder, overwritten below
+    one_q = bn.ints_to_array([bn.to_mont(1, bn.Q)])[0]
+    jac[1:, 8:] = one_q                                        # z = 1 for finite points
+    jac[0, 4:8] = one_q                                        # identity = (0, 1, 0)
+    assert np.array_equal(zk.g1_to_bytes(jac), g["enc_bytes"])
+    assert np.array_equal(zk.g1_to_evm_bytes(jac), g["enc_evm"])

@@ -107,3 +107,28 @@ def test_permute_expression_pair_satisfies_the_lookup_constraints():
     assert all(a[i] == s[i] or a[i] == a[i - 1] for i in range(1, usable))
     with pytest.raises(ValueError, match="ConstraintSystemFailure"):
         ps.permute_expression_pair([R - 5] + inp[1:] + pad, tab + pad, bf)
+
+
+def test_restatements_match_the_definition_golden():
+    """tests/golden/prover_steps_kat.npz is produced from the definitions (oracle/make_golden.py
+    prover_steps); the statement-by-statement restatements must reproduce it."""
+    from pathlib import Path
+
+    import numpy as np
+    g = np.load(Path(__file__).parent / "golden" / "prover_steps_kat.npz")
+    I, one = bn.fr_array_to_canonical, lambda a: bn.fr_array_to_canonical(a[None, :])[0]
+    assert ps.batch_invert(I(g["inv_in"])) == I(g["inv_out"])
+    assert ps.eval_polynomial(I(g["eval_poly"]), one(g["eval_point"])) == one(g["eval_out"])
+    assert ps.kate_division(I(g["eval_poly"]), one(g["kate_b"])) == I(g["kate_out"])
+    k, n_cols, chunk, bf = (int(x) for x in g["perm_shape"])
+    beta, gamma = I(g["perm_beta_gamma"])
+    omega = pow(bn.FR_ROOT_OF_UNITY, 1 << (28 - k), R)
+    zs = ps.permutation_products([I(v) for v in g["perm_values"]], [I(v) for v in g["perm_sigma"]], chunk, omega, beta,
+                                 gamma, bf)
+    assert zs == [I(z) for z in g["perm_z"]]
+    ci, ct, pi, pt = (I(c) for c in g["lookup_cols"])
+    assert ps.lookup_product(ci, ct, pi, pt, beta, gamma, bf) == I(g["lookup_z"])
+    pts = bn.g1_affine_array_to_points(g["enc_points"])
+    assert [bn.g1_to_bytes(p) for p in pts] == [bytes(r) for r in g["enc_bytes"]]
+    assert [bn.g1_to_evm_bytes(p) for p in pts] == [bytes(r) for r in g["enc_evm"]]
+    assert [bn.g1_from_bytes(bytes(r)) for r in g["enc_bytes"]] == pts
