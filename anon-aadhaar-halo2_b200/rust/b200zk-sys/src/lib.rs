@@ -58,7 +58,10 @@ extern "C" {
     pub fn b200zk_ntt4_gather_rows_dev(d_recv: *const c_void, d_out: *mut c_void, log_n: u32, log_n1: u32, world: u32, stream: *mut c_void) -> c_int;
     pub fn b200zk_msm_g1(scalars: *const u64, bases: *const u64, n: usize, out_xyz: *mut u64) -> c_int;
     pub fn b200zk_bases_register(bases: *const u64, n: usize, handle_out: *mut u64) -> c_int;
+    pub fn b200zk_bases_register_ex(bases: *const u64, n: usize, precompute_windows: c_int, handle_out: *mut u64) -> c_int;
     pub fn b200zk_bases_evict(handle: u64) -> c_int;
+    pub fn b200zk_msm_g1_registered_many(handle: u64, scalars: *const u64, stride: usize, count: usize, n: usize, out_xyz: *mut u64) -> c_int;
+    pub fn b200zk_msm_g1_registered_dev(handle: u64, d_scalars: *const c_void, stride: usize, count: usize, n: usize, d_out_xyz: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn b200zk_msm_g1_registered(handle: u64, scalars: *const u64, n: usize, out_xyz: *mut u64) -> c_int;
     pub fn b200zk_msm_g1_dev(d_scalars: *const c_void, d_bases: *const c_void, n: usize, out_xyz: *mut u64, stream: *mut c_void) -> c_int;
     pub fn b200zk_msm_g1_dev_async(d_scalars: *const c_void, d_bases: *const c_void, n: usize, d_out_xyz: *mut c_void, stream: *mut c_void) -> c_int;
@@ -78,6 +81,15 @@ extern "C" {
     pub fn b200zk_g1_affine_to_bytes(points_xy: *const u64, count: usize, out32: *mut u8) -> c_int;
     pub fn b200zk_g1_to_evm_bytes(points_xyz: *const u64, count: usize, out64: *mut u8) -> c_int;
     pub fn b200zk_g1_affine_from_bytes(in32: *const u8, count: usize, points_xy: *mut u64) -> c_int;
+
+    // measurement and test support
+    pub fn b200zk_gen_scalars_dev(d_out: *mut c_void, n: usize, seed: u64, start: usize) -> c_int;
+    pub fn b200zk_gen_points_dev(d_out: *mut c_void, n: usize, seed: u64, start: usize) -> c_int;
+    pub fn b200zk_modmul_peak(iters: u32, modmul_per_s_out: *mut f64) -> c_int;
+    pub fn b200zk_msm_profile(enable: c_int) -> c_int;
+    pub fn b200zk_msm_tune(max_chunk: u32, max_seglen: u32, force_window_bits: u32) -> c_int;
+    pub fn b200zk_msm_last_stages(ms_out: *mut f32, capacity: c_int, info_out: *mut u64) -> c_int;
+    pub fn b200zk_kernel_launches() -> u64;
 
     pub fn b200zk_dev_alloc(n_elems: usize, handle_out: *mut u64) -> c_int;
     pub fn b200zk_dev_free(handle: u64) -> c_int;
