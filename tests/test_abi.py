@@ -61,3 +61,14 @@ def test_product_does_not_import_oracle():
         if re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M) or "halo2_oracle" in text or "c_oracle" in text:
             offenders.append(str(path))
     assert not offenders, offenders
+
+
+def test_rust_ffi_block_declares_every_header_symbol():
+    """anon-aadhaar-halo2_b200/rust/b200zk-sys/src/lib.rs cannot be compiled here (no cargo), so at
+    least keep its hand-written `extern "C"` block in step with include/b200zk.h."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    header = set(re.findall(r"\b(b200zk_[a-z0-9_]+)\s*\(", (root / "include" / "b200zk.h").read_text()))
+    rust = set(re.findall(r"pub fn (b200zk_[a-z0-9_]+)", (root / "anon-aadhaar-halo2_b200" / "rust" / "b200zk-sys" / "src" / "lib.rs").read_text()))
+    assert header == rust, (sorted(header - rust), sorted(rust - header))
