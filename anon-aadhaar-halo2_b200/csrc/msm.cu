@@ -298,7 +298,7 @@ __device__ __forceinline__ uint32_t find_key(const uint32_t* __restrict__ start,
     return lo;
 }
 
-__global__ void __launch_bounds__(128) msm_accum_kernel(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128, 5) msm_accum_kernel(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                         const uint32_t* __restrict__ start, uint32_t nkeys, uint32_t npairs,
                                                         uint32_t L, G1Xyzz* __restrict__ buckets,
                                                         uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt,
