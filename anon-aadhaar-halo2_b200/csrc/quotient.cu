@@ -408,7 +408,9 @@ int b200zk_quotient_graph(const b200zk_graph* g, const b200zk_quotient_env* env,
         else if (g->n_intermediates <= 256) quotient_graph_kernel<256><<<blocks, 128, 0, s>>>(G);
         else quotient_graph_kernel<1024><<<blocks, 128, 0, s>>>(G);
         ZK_LAUNCH_CHECK();
-        ZK_CUDA(cudaStreamSynchronize(s));
+        // no synchronisation: inputs were staged from pageable memory (copied before the call
+        // returns), outputs stay on the device, and the next call is ordered behind this one on the
+        // library stream (24 lookups = 48 launches per proof: a sync each would cost more than the kernels)
     });
 }
 
@@ -470,7 +472,6 @@ int b200zk_quotient_permutation(const b200zk_quotient_env* env, uint64_t values_
         env_range(env, P.begin, P.count);
         quotient_permutation_kernel<<<(unsigned)((P.count + 127) / 128), 128, 0, s>>>(P);
         ZK_LAUNCH_CHECK();
-        ZK_CUDA(cudaStreamSynchronize(s));
     });
 }
 
@@ -501,7 +502,6 @@ int b200zk_quotient_lookup(const b200zk_quotient_env* env, uint64_t values_handl
         env_range(env, L.begin, L.count);
         quotient_lookup_kernel<<<(unsigned)((L.count + 127) / 128), 128, 0, s>>>(L);
         ZK_LAUNCH_CHECK();
-        ZK_CUDA(cudaStreamSynchronize(s));
     });
 }
 

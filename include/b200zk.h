@@ -205,7 +205,10 @@ typedef struct {
     uint64_t range_begin, range_len;
 } b200zk_quotient_env;
 
-/* out[idx] = graph.evaluate(idx, previous_value = previous[idx] or 0 when the handle is 0)
+/* The three quotient entry points are asynchronous on the library's stream (their results stay in
+ * device columns); b200zk_dev_download, or any host-result call, synchronises.
+ *
+ * out[idx] = graph.evaluate(idx, previous_value = previous[idx] or 0 when the handle is 0)
  * for every idx of the extended domain; rotation r reads index
  * (idx + r * 2^(ext_k - k)) mod 2^ext_k.  `out` may equal `previous` (the custom-gate
  * loop of evaluate_h: values[idx] = custom_gates.evaluate(.., &values[idx], ..)). */
