@@ -396,6 +396,15 @@ class ProverHotPath:
         self.lib.b200zk_bases_evict(self.h_bases)
         for v in self.ext_views + self.fixed + self.sigma + [self.l0, self.l_last, self.l_active]:
             v.free()
+        for q, (col, views) in getattr(self, "pk_coset", {}).items():
+            for v in views:
+                v.free()
+            col.free()
+        for v in getattr(self, "cos_views", []):
+            v.free()
+        for name in ("lag_pad", "coef_all", "cos", "h_mine", "h_all"):
+            if hasattr(self, name):
+                getattr(self, name).free()
         for c in (self.pk_cols, self.lag, self.instance_coeff, self.ext, self.values, self.table, self.h_coeff,
                   self.points):
             c.free()
