@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __rest
 // precomputed table, with the sign of the digit in bit 31.
 __global__ void msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n, uint32_t c, uint32_t nwin,
                                    uint32_t key_windows, uint32_t table_stride, uint32_t sub_bits,
-                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+                                   uint32_t index_offset, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t cw = blockIdx.y >> sub_bits;             // col * nwin + w
     const uint32_t sub = blockIdx.y & ((1u << sub_bits) - 1u);
@@ -277,7 +277,7 @@ __global__ void msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n,
     base = __shfl_sync(0xffffffffu, base, leader);
     if (!mine) return;
     const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    sorted[pos] = ((uint32_t)i + w * table_stride) | (d < 0 ? 0x80000000u : 0u);
+    sorted[pos] = ((uint32_t)i + index_offset + w * table_stride) | (d < 0 ? 0x80000000u : 0u);
 }
 
 constexpr uint32_t MSM_PAD_KEY = 0xffffffffu;   // padding lane (real keys are < 2^31)
@@ -298,6 +298,10 @@ __device__ __forceinline__ uint32_t find_key(const uint32_t* __restrict__ start,
     return lo;
 }
 
+// ADD = false: buckets were cleared, a closed run is stored.  ADD = true (a later point range of the
+// same MSM, b200zk_msm_g1_registered's upload pipeline): a run that closes inside the chunk
+// continues from what the earlier ranges left in the bucket.
+template <bool ADD>
 __global__ void __launch_bounds__(128, 5) msm_accum_kernel(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                         const uint32_t* __restrict__ start, uint32_t nkeys, uint32_t npairs,
                                                         uint32_t L, G1Xyzz* __restrict__ buckets,
@@ -309,7 +313,9 @@ __global__ void __launch_bounds__(128, 5) msm_accum_kernel(const G1Affine* __res
     const uint32_t end = min(begin + L, npairs);
     uint32_t key = find_key(start, nkeys, begin);
     uint32_t run_end = __ldg(start + key + 1);
-    G1Xyzz acc = G1Xyzz::identity();
+    // ADD: the thread that will close a run (the only level-0 writer of that bucket) starts from
+    // what the earlier point ranges left there, so the hot loop carries no extra addition
+    G1Xyzz acc = (ADD && run_end <= end) ? ld_xyzz(buckets + key) : G1Xyzz::identity();
     // software prefetch of the next point
     uint32_t e = __ldg(sorted + begin);
     G1Affine nxt;
@@ -326,11 +332,11 @@ __global__ void __launch_bounds__(128, 5) msm_accum_kernel(const G1Affine* __res
         }
         if (pos >= run_end) {
             st_xyzz(buckets + key, acc);
-            acc = G1Xyzz::identity();
             do {
                 ++key;
                 run_end = __ldg(start + key + 1);
             } while (pos >= run_end);
+            acc = (ADD && run_end <= end) ? ld_xyzz(buckets + key) : G1Xyzz::identity();
         }
         if (negate) p.y = p.y.neg();
         acc.add_affine(p);
@@ -546,6 +552,13 @@ static uint32_t g_msm_max_chunk = 128;   // tunable (b200zk_msm_tune)
 static uint32_t g_msm_max_seglen = 64;    // measured: 104 -> 64 takes the 242-column reduce from 3.5 to 3.1 ms
 static uint32_t g_msm_force_c = 0;
 // scatter sub-range bits; B200ZK_MSM_SUB_BITS overrides the automatic choice (experiments only)
+// upload pipeline of b200zk_msm_g1_registered (one large host-side commit): number of point
+// ranges and the size from which it is used
+constexpr size_t MSM_MAX_PARTS = 16;
+static size_t g_msm_pipe_parts = getenv("B200ZK_MSM_PIPE_PARTS") ? (size_t)atoi(getenv("B200ZK_MSM_PIPE_PARTS")) : 4;
+static size_t g_msm_pipe_min_n = getenv("B200ZK_MSM_PIPE_MIN_N") ? (size_t)atoll(getenv("B200ZK_MSM_PIPE_MIN_N")) : ((size_t)1 << 22);
+static cudaStream_t g_msm_copy_stream = nullptr;
+static cudaEvent_t g_msm_part_ev[MSM_MAX_PARTS + 1];
 static uint32_t g_msm_force_sub = getenv("B200ZK_MSM_SUB_BITS") ? (uint32_t)atoi(getenv("B200ZK_MSM_SUB_BITS")) : 0xffffffffu;
 static cudaEvent_t g_msm_ev[MSM_ST_COUNT];
 static bool g_msm_ev_made = false, g_msm_ev_valid[MSM_ST_COUNT];
@@ -648,8 +661,17 @@ __global__ void __launch_bounds__(256) msm_group_sum_kernel(const G1Xyzz* __rest
 
 // `count` MSMs over the same n bases: column j uses scalars d_scalars + j * scalar_stride and
 // writes d_out[j].  All inputs device-resident.  `pre` (optional) is a per-window table.
+// One MSM may be fed in consecutive point ranges that share the bucket set (a host-side commit
+// whose scalars are still arriving over PCIe): `first` clears the buckets, later parts add into
+// them, `last` runs the bucket reduction.  index_offset = first point of the range.
+struct MsmPart {
+    bool first = true, last = true;
+    uint32_t index_offset = 0;
+};
+
 static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, size_t count,
-                       const G1Affine* d_bases, size_t n, const MsmPre* pre, G1Jacobian* d_out, cudaStream_t s) {
+                       const G1Affine* d_bases, size_t n, const MsmPre* pre, G1Jacobian* d_out, cudaStream_t s,
+                       const MsmPart& part = MsmPart()) {
     ZK_REQUIRE(n < ((size_t)1 << 28), "MSM size must be below 2^28 points");
     if (count == 0) return;
     if (n == 0) {
@@ -682,6 +704,8 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     const size_t red_entries = (size_t)segs_per_group * groups;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_buckets = carve((size_t)nkeys * sizeof(G1Xyzz));   // first: same place for every part of an MSM
+    const size_t o_win = carve(groups * sizeof(G1Xyzz));
     const size_t o_hist = carve(((size_t)nkeys + 1) * 4);
     const size_t o_start = carve(((size_t)nkeys + 1) * 4);
     const size_t o_cursor = carve(((size_t)nkeys + 1) * 4);
@@ -689,8 +713,6 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     const size_t o_total = carve(256);
     const size_t o_sorted = carve(max_pairs * 4);
     const size_t o_digits = carve(max_pairs * 4);
-    const size_t o_buckets = carve((size_t)nkeys * sizeof(G1Xyzz));
-    const size_t o_win = carve(groups * sizeof(G1Xyzz));
     char* base = (char*)c.msm_work.get(off);
     uint32_t* hist = (uint32_t*)(base + o_hist);
     uint32_t* start = (uint32_t*)(base + o_start);
@@ -705,8 +727,10 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     StageTimer T(c, s);
     // ---- 1-3: sort (bucket, point) pairs
     ZK_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nkeys + 1) * 4, s));
-    ZK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nkeys * sizeof(G1Xyzz), s));
-    ZK_CUDA(cudaMemsetAsync(win, 0, groups * sizeof(G1Xyzz), s));
+    if (part.first) {
+        ZK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nkeys * sizeof(G1Xyzz), s));
+        ZK_CUDA(cudaMemsetAsync(win, 0, groups * sizeof(G1Xyzz), s));
+    }
     const unsigned sblocks = (unsigned)((n + 255) / 256);
     T.mark(MSM_ST_HIST);
     msm_hist_kernel<<<dim3(sblocks, (unsigned)count), 256, 0, s>>>(d_scalars, scalar_stride, n, cbits, nwin,
@@ -725,7 +749,7 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     uint32_t sub_bits = (pre && n * 4 > ((size_t)16 << 20) && cbits > 2 && count * nwin * 2 <= 65535) ? 1u : 0u;
     if (g_msm_force_sub != 0xffffffffu) sub_bits = std::min<uint32_t>(g_msm_force_sub, cbits - 1);
     msm_scatter_kernel<<<dim3(sblocks, (unsigned)((count * nwin) << sub_bits)), 256, 0, s>>>(
-        digits, n, cbits, nwin, key_windows, pre ? (uint32_t)pre->n_reg : 0u, sub_bits, cursor, sorted);
+        digits, n, cbits, nwin, key_windows, pre ? (uint32_t)pre->n_reg : 0u, sub_bits, part.index_offset, cursor, sorted);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SYNC);
     uint32_t npairs = 0;
@@ -754,13 +778,21 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     // ---- 4: accumulate
     T.mark(MSM_ST_ACCUM);
     if (npairs > 0) {
-        msm_accum_kernel<<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start, nkeys,
-                                                                 npairs, L, buckets, keyA, ptA, nthreads0);
+        if (part.first)
+            msm_accum_kernel<false><<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start,
+                                                                            nkeys, npairs, L, buckets, keyA, ptA, nthreads0);
+        else
+            msm_accum_kernel<true><<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start,
+                                                                           nkeys, npairs, L, buckets, keyA, ptA, nthreads0);
         ZK_LAUNCH_CHECK();
         T.mark(MSM_ST_COMBINE);
         run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, buckets, s);
     }
 
+    if (!part.last) {
+        T.mark(MSM_ST_END);
+        return;
+    }
     // ---- 5: per-bucket-set running sums, then keyed reduction with key = bucket set
     T.mark(MSM_ST_REDUCE);
     {
@@ -885,10 +917,38 @@ static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stri
     cudaStream_t s = c.stream;
     Fr* ds = (Fr*)c.msm_scalars.get(std::max<size_t>(n * count, 1) * sizeof(Fr));
     G1Jacobian* dout = (G1Jacobian*)c.misc.get(count * sizeof(G1Jacobian));
+    MsmPre pre{t->table, t->n, t->c, t->nwin};
+    // One large commit with a window table: feed it in point ranges that share the bucket set,
+    // so the upload of range p+1 runs under the sort + accumulation of range p.
+    const size_t parts = (count == 1 && t->table && n >= g_msm_pipe_min_n) ? std::min<size_t>(g_msm_pipe_parts, MSM_MAX_PARTS) : 1;
+    if (parts > 1) {
+        if (!g_msm_copy_stream) {
+            ZK_CUDA(cudaStreamCreateWithFlags(&g_msm_copy_stream, cudaStreamNonBlocking));
+            for (auto& e : g_msm_part_ev) ZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const size_t per = align_up((n + parts - 1) / parts, 256);
+        ZK_CUDA(cudaEventRecord(g_msm_part_ev[MSM_MAX_PARTS], s));   // earlier users of the staging buffer
+        ZK_CUDA(cudaStreamWaitEvent(g_msm_copy_stream, g_msm_part_ev[MSM_MAX_PARTS], 0));
+        size_t nparts = 0;
+        for (size_t b = 0; b < n; b += per, ++nparts) {
+            const size_t len = std::min(per, n - b);
+            ZK_CUDA(cudaMemcpyAsync(ds + b, scalars + 4 * b, len * sizeof(Fr), cudaMemcpyHostToDevice, g_msm_copy_stream));
+            ZK_CUDA(cudaEventRecord(g_msm_part_ev[nparts], g_msm_copy_stream));
+        }
+        for (size_t p = 0; p < nparts; ++p) {
+            const size_t b = p * per, len = std::min(per, n - b);
+            ZK_CUDA(cudaStreamWaitEvent(s, g_msm_part_ev[p], 0));
+            MsmPart part;
+            part.first = p == 0; part.last = p + 1 == nparts; part.index_offset = (uint32_t)b;
+            msm_device(c, ds + b, len, 1, t->d, len, &pre, dout, s, part);
+        }
+        ZK_CUDA(cudaMemcpyAsync(out_xyz, dout, sizeof(G1Jacobian), cudaMemcpyDeviceToHost, s));
+        ZK_CUDA(cudaStreamSynchronize(s));
+        return;
+    }
     if (n)
         ZK_CUDA(cudaMemcpy2DAsync(ds, n * sizeof(Fr), scalars, stride * sizeof(Fr), n * sizeof(Fr), count,
                                   cudaMemcpyHostToDevice, s));
-    MsmPre pre{t->table, t->n, t->c, t->nwin};
     msm_device(c, ds, n, count, t->d, n, t->table ? &pre : nullptr, dout, s);
     ZK_CUDA(cudaMemcpyAsync(out_xyz, dout, count * sizeof(G1Jacobian), cudaMemcpyDeviceToHost, s));
     ZK_CUDA(cudaStreamSynchronize(s));
@@ -950,6 +1010,14 @@ int b200zk_msm_tune(uint32_t max_chunk, uint32_t max_seglen, uint32_t force_wind
         g_msm_max_chunk = max_chunk;
         g_msm_max_seglen = max_seglen;
         g_msm_force_c = force_window_bits;
+    });
+}
+
+int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n) {
+    return guarded([&] {
+        ZK_REQUIRE(parts >= 1 && parts <= MSM_MAX_PARTS, "parts out of range");
+        g_msm_pipe_parts = parts;
+        g_msm_pipe_min_n = min_n;
     });
 }
 

@@ -331,6 +331,11 @@ int b200zk_msm_profile(int enable);
  * bucket segment one thread reduces, and a forced window size (0 = cost model). */
 int b200zk_msm_tune(uint32_t max_chunk, uint32_t max_seglen, uint32_t force_window_bits);
 int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]);
+/* Upload pipeline of b200zk_msm_g1_registered: a single host-side commit of at least `min_n`
+ * scalars against a window table is fed in `parts` point ranges that share one bucket set, so
+ * the PCIe upload of range p+1 runs under the sort + accumulation of range p (same group
+ * element).  parts = 1 disables it.  Defaults: 4 parts from 2^22 scalars. */
+int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n);
 /* Number of kernels launched by this library since init (for bench.py gpu_launches). */
 uint64_t b200zk_kernel_launches(void);
 

@@ -194,3 +194,34 @@ def test_commit_many_prover_shape(zk):
     got = [jac_affine(p) for p in params.commit_lagrange_many(cols)]
     assert got == [jac_affine(co.best_multiexp(cols[j], gl)) for j in range(cnt)]
     params.close()
+
+
+@pytest.mark.parametrize("parts,n", [(2, 1 << 12), (3, 5000), (4, (1 << 14) + 77), (16, 300), (5, 1 << 16)])
+def test_commit_upload_pipeline_same_point(zk, parts, n):
+    """b200zk_msm_g1_registered fed in point ranges that share the bucket set (the upload
+    pipeline of large host-side commits): the same group element as the one-shot path and as
+    the oracle, with scalars that force later ranges to add into buckets earlier ranges filled
+    (few distinct digits), empty ranges of buckets, repeated and identity bases."""
+    lib = zk.load()
+    g = co.gen_points(71, n)
+    g[5] = g[4]
+    g[11] = 0
+    s = co.gen_scalars(72 + parts, n)
+    m = n // 8
+    s[n // 2:n // 2 + m] = bn.fr_array_from_canonical([bn.R - 1] * m)       # one bucket per window, every range
+    s[m:2 * m] = 0                                                          # dropped digits
+    s[n - m:] = bn.fr_array_from_canonical([(5 * i) % 97 for i in range(m)])
+    want = jac_affine(co.best_multiexp(s, g))
+    params = zk.ParamsKZG(g, g)
+    try:
+        zk.check(lib.b200zk_msm_upload_pipeline(1, 1 << 22))
+        one_shot = jac_affine(params.commit(s))
+        zk.check(lib.b200zk_msm_upload_pipeline(parts, 1))
+        piped = jac_affine(params.commit(s))
+        piped_short = jac_affine(params.commit(s[: n - 3]))          # ragged last range, fewer scalars than bases
+    finally:
+        zk.check(lib.b200zk_msm_upload_pipeline(4, 1 << 22))
+        params.close()
+    assert one_shot == want
+    assert piped == want
+    assert piped_short == jac_affine(co.best_multiexp(s[: n - 3], g[: n - 3]))
