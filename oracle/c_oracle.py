@@ -100,3 +100,11 @@ def gen_points(seed: int, n: int, start: int = 0, threads=None) -> np.ndarray:
     out = np.zeros((n, 8), dtype=np.uint64)
     lib().orc_gen_points(_p(out), C.c_size_t(n), C.c_uint64(seed), C.c_size_t(start), threads or host_threads())
     return out
+
+
+def g1_generator_mul(scalars: np.ndarray, threads=None) -> np.ndarray:
+    """[s_i] G for Montgomery scalars (n, 4) -> affine Montgomery points (n, 8)."""
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    out = np.zeros((scalars.shape[0], 8), dtype=np.uint64)
+    lib().orc_g1_generator_mul(_p(scalars), C.c_size_t(scalars.shape[0]), _p(out), threads or host_threads())
+    return out

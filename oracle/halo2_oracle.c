@@ -542,3 +542,46 @@ void orc_gen_points(uint64_t* out, size_t n, uint64_t seed, size_t start, int th
     }
     for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
 }
+
+/* ------------------------------------------------------- local KZG setup (test SRS) */
+/* out[i] = [scalars[i]] G, G = (1, 2): scalars Montgomery Fr, points affine Montgomery.
+ * The group elements a `ParamsKZG::setup(k, rng)` produces ([s^i] G and [L_i(s)] G,
+ * poly/kzg/commitment.rs) are determined by the scalars; this is plain double-and-add over a
+ * table of [2^b] G. */
+typedef struct { const uint64_t* sc; uint64_t* out; size_t lo, hi; const g1a* tbl; } gmul_job;
+static void* gmul_thread(void* arg) {
+    gmul_job* j = (gmul_job*)arg;
+    for (size_t i = j->lo; i < j->hi; ++i) {
+        uint64_t s[4];
+        f_from_mont(&FR, s, (const fe*)(j->sc + 4 * i));
+        g1j acc;
+        g1j_set_id(&acc);
+        for (int b = 0; b < 254; ++b)
+            if ((s[b >> 6] >> (b & 63)) & 1) g1j_add_affine(&acc, &acc, &j->tbl[b]);
+        g1j_to_affine((g1a*)(j->out + 8 * i), &acc);
+    }
+    return NULL;
+}
+void orc_g1_generator_mul(const uint64_t* scalars, size_t n, uint64_t* out, int threads) {
+    static g1a tbl[254];
+    g1j p;
+    p.x = FQ.one;
+    f_dbl(&FQ, &p.y, &FQ.one);
+    p.z = FQ.one;
+    for (int b = 0; b < 254; ++b) {
+        g1j_to_affine(&tbl[b], &p);
+        g1j_double(&p, &p);
+    }
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    pthread_t th[64];
+    gmul_job jobs[64];
+    size_t chunk = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        size_t lo = (size_t)t * chunk, hi = lo + chunk > n ? n : lo + chunk;
+        if (lo > n) lo = n;
+        jobs[t] = (gmul_job){scalars, out, lo, hi, tbl};
+        pthread_create(&th[t], NULL, gmul_thread, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+}

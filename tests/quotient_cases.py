@@ -42,7 +42,7 @@ def square_case(k=4, seed=1):
     """SquareCircuit shape: 1 fixed, 2 advice, 1 instance, permutation over
     [advice0, advice1, instance0], degree 3 (chunk 1, 3 sets), blinding_factors 5."""
     rnd = random.Random(seed)
-    domain = h.EvaluationDomain(4, k)      # cs.degree() = 3 -> j = degree + 1
+    domain = h.EvaluationDomain(3, k)      # EvaluationDomain::new(cs.degree(), k): ext_k = k + 1, two quotient pieces (contract.sol:11-12)
     N = domain.extended_n
     bf = 5
     l0, l_last, l_blind, l_active = lagrange_cols(domain, bf)
@@ -66,7 +66,7 @@ def wide_case(k=6, seed=2, n_advice=6, n_fixed=4, n_lookups=2):
     chunk_len 3 (degree 5) and two lookups."""
     rnd = random.Random(seed)
     degree = 5
-    domain = h.EvaluationDomain(degree + 1, k)
+    domain = h.EvaluationDomain(degree, k)
     N = domain.extended_n
     bf = 5
     A = lambda i, r=0: q.Advice(i % n_advice, r)

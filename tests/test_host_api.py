@@ -20,7 +20,7 @@ def test_evaluation_domain_constants_match_oracle():
         assert f(d.g_coset) == o.g_coset and f(d.g_coset_inv) == o.g_coset_inv
         assert bn.fr_array_to_canonical(d.t_evaluations) == o.t_evaluations
     # RSA-SHA256 shape of the reference (src/lib.rs:444: k = 15; degree 4 -> ext_k = 17)
-    assert EvaluationDomain(5, 15).extended_k == 17
+    assert EvaluationDomain(4, 15).extended_k == 17
 
 
 def test_length_assertions_mirror_upstream():

@@ -12,7 +12,7 @@ F = bn.fr_array_from_canonical
 
 
 def run_device(zk, case, gates, lgraphs):
-    d = zk.EvaluationDomain(case["degree"] + 1, case["k"])
+    d = zk.EvaluationDomain(case["degree"], case["k"])
     col = lambda ints: zk.DeviceColumn.from_host(F(ints))
     flat = lambda g: zk.FlatGraph(**g.to_flat())
     pk = zk.ProvingKeyCosets(
@@ -60,7 +60,7 @@ def test_sharded_extended_domain_equals_whole(zk):
 
     case = wide_case(k=6, seed=5)
     values, _, gates, lgraphs = oracle_evaluate_h(case)
-    d = zk.EvaluationDomain(case["degree"] + 1, case["k"])
+    d = zk.EvaluationDomain(case["degree"], case["k"])
     col = lambda ints: zk.DeviceColumn.from_host(F(ints))
     flat = lambda g: zk.FlatGraph(**g.to_flat())
     pk = zk.ProvingKeyCosets(
