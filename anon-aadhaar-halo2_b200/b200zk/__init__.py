@@ -23,9 +23,12 @@ from .api import (  # noqa: F401
     g1_sum,
     g1_to_bytes,
     g1_to_evm_bytes,
+    host_alloc_fr,
+    host_free,
     init,
     kernel_launches,
     modmul_peak,
+    pinned,
     shutdown,
 )
 from .quotient import (  # noqa: F401,E402

@@ -102,6 +102,10 @@ def load() -> C.CDLL:
         "b200zk_modmul_peak": ([u32, C.POINTER(C.c_double)], C.c_int),
         "b200zk_kernel_launches": ([], u64),
         "b200zk_msm_profile": ([C.c_int], C.c_int),
+        "b200zk_host_register": ([vp, sz], C.c_int),
+        "b200zk_host_unregister": ([vp], C.c_int),
+        "b200zk_host_alloc": ([sz, C.POINTER(C.c_void_p)], C.c_int),
+        "b200zk_host_free": ([vp], C.c_int),
         "b200zk_msm_tune": ([u32, u32, u32], C.c_int),
         "b200zk_msm_upload_pipeline": ([u32, sz], C.c_int),
         "b200zk_msm_last_stages": ([C.POINTER(C.c_float), C.c_int, u64p], C.c_int),

@@ -55,6 +55,42 @@ def shutdown() -> None:
     check(load().b200zk_shutdown())
 
 
+class pinned:
+    """Page-lock a numpy buffer for the duration of a `with` block (b200zk_host_register): what a
+    Rust shim does once for the `Vec<Fr>`s a proof keeps, so host-pointer calls transfer at the full
+    PCIe rate and the MSM upload pipeline can overlap its copies."""
+
+    def __init__(self, a: np.ndarray):
+        assert a.flags.c_contiguous
+        self.a = a
+
+    def __enter__(self):
+        check(load().b200zk_host_register(C.c_void_p(self.a.ctypes.data), self.a.nbytes))
+        return self.a
+
+    def __exit__(self, *exc):
+        check(load().b200zk_host_unregister(C.c_void_p(self.a.ctypes.data)))
+        return False
+
+
+def host_alloc_fr(n: int, width: int = 4) -> np.ndarray:
+    """An (n, width) uint64 array in page-locked memory from b200zk_host_alloc; release it with
+    host_free."""
+    p = C.c_void_p(0)
+    check(load().b200zk_host_alloc(max(n * width * 8, 8), C.byref(p)))
+    buf = (C.c_uint64 * (n * width)).from_address(p.value)
+    a = np.frombuffer(buf, dtype=np.uint64).reshape(n, width)
+    _host_allocs[a.ctypes.data] = p.value
+    return a
+
+
+def host_free(a: np.ndarray) -> None:
+    check(load().b200zk_host_free(C.c_void_p(_host_allocs.pop(a.ctypes.data))))
+
+
+_host_allocs = {}
+
+
 def kernel_launches() -> int:
     return int(load().b200zk_kernel_launches())
 

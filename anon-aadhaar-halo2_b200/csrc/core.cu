@@ -3,6 +3,7 @@
 #include "../../include/b200zk.h"
 #include "common.cuh"
 #include <cstdlib>
+#include <set>
 #include "ec.cuh"
 #include "ntt.cuh"
 
@@ -131,6 +132,9 @@ __global__ void __launch_bounds__(256) modmul_peak_kernel(Fq* out, uint32_t iter
 
 using namespace zk;
 
+// page-locked host memory handed out / registered through the ABI (b200zk_host_*)
+static std::set<void*> g_host_registered, g_host_allocated;
+
 extern "C" {
 
 uint32_t b200zk_abi_version(void) { return 1; }
@@ -163,6 +167,10 @@ int b200zk_shutdown(void) {
             if (kv.second.owned) cudaFree(kv.second.p);
         c.buffers.clear();
         c.pinned.release();
+        for (void* p : g_host_registered) cudaHostUnregister(p);
+        for (void* p : g_host_allocated) cudaFreeHost(p);
+        g_host_registered.clear();
+        g_host_allocated.clear();
         cudaStreamDestroy(c.stream);
         c.stream = nullptr;
         c.ready = false;
@@ -170,6 +178,45 @@ int b200zk_shutdown(void) {
 }
 
 uint64_t b200zk_kernel_launches(void) { return g_launches.load(); }
+
+int b200zk_host_register(void* ptr, size_t bytes) {
+    return guarded([&] {
+        ZK_REQUIRE(ptr && bytes, "null or empty host buffer");
+        ensure_init();
+        ZK_REQUIRE(!g_host_registered.count(ptr) && !g_host_allocated.count(ptr), "host buffer already page-locked");
+        ZK_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+        g_host_registered.insert(ptr);
+    });
+}
+
+int b200zk_host_unregister(void* ptr) {
+    return guarded([&] {
+        ZK_REQUIRE(g_host_registered.count(ptr), "host buffer was not registered");
+        cudaStreamSynchronize(ctx().stream);
+        ZK_CUDA(cudaHostUnregister(ptr));
+        g_host_registered.erase(ptr);
+    });
+}
+
+int b200zk_host_alloc(size_t bytes, void** ptr_out) {
+    return guarded([&] {
+        ZK_REQUIRE(ptr_out && bytes, "null argument or empty allocation");
+        ensure_init();
+        void* p = nullptr;
+        ZK_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocPortable));
+        g_host_allocated.insert(p);
+        *ptr_out = p;
+    });
+}
+
+int b200zk_host_free(void* ptr) {
+    return guarded([&] {
+        ZK_REQUIRE(g_host_allocated.count(ptr), "not a b200zk_host_alloc allocation");
+        cudaStreamSynchronize(ctx().stream);
+        ZK_CUDA(cudaFreeHost(ptr));
+        g_host_allocated.erase(ptr);
+    });
+}
 
 int b200zk_gen_scalars_dev(void* d_out, size_t n, uint64_t seed, size_t start) {
     return guarded([&] {

@@ -92,6 +92,12 @@ extern "C" {
     pub fn b200zk_msm_upload_pipeline(parts: u32, min_n: usize) -> c_int;
     pub fn b200zk_kernel_launches() -> u64;
 
+    // page-locked host memory
+    pub fn b200zk_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
+    pub fn b200zk_host_unregister(ptr: *mut c_void) -> c_int;
+    pub fn b200zk_host_alloc(bytes: usize, ptr_out: *mut *mut c_void) -> c_int;
+    pub fn b200zk_host_free(ptr: *mut c_void) -> c_int;
+
     pub fn b200zk_dev_alloc(n_elems: usize, handle_out: *mut u64) -> c_int;
     pub fn b200zk_dev_free(handle: u64) -> c_int;
     pub fn b200zk_dev_view(parent: u64, offset: usize, n_elems: usize, handle_out: *mut u64) -> c_int;

@@ -39,6 +39,19 @@ const char* b200zk_last_error(void);
 /* ABI version of this header (checked by the bindings). */
 uint32_t b200zk_abi_version(void);
 
+/* ---- host memory ------------------------------------------------------------------- */
+/* Every host-pointer entry point accepts pageable memory (a Rust `Vec<Fr>`), but the driver then
+ * stages each transfer through its own bounce buffer at a fraction of the PCIe rate and the
+ * upload pipeline of b200zk_msm_g1_registered cannot overlap it.  A shim that keeps a buffer for
+ * the whole proof (the polynomials of `create_proof`, the SRS during registration) page-locks it
+ * once with b200zk_host_register; a caller that chooses its allocator takes page-locked memory
+ * from b200zk_host_alloc.  Registration does not transfer ownership: the caller unregisters
+ * before freeing.  Everything still registered or allocated is released by b200zk_shutdown. */
+int b200zk_host_register(void* ptr, size_t bytes);
+int b200zk_host_unregister(void* ptr);
+int b200zk_host_alloc(size_t bytes, void** ptr_out);
+int b200zk_host_free(void* ptr);
+
 /* ---- NTT: arithmetic::best_fft and EvaluationDomain -------------------------------- */
 /* halo2_proofs/src/arithmetic.rs `best_fft::<Fr>(a, omega, log_n)`: in place,
  * natural order in and out, a'[i] = sum_j a[j] * omega^(i*j). */

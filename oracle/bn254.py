@@ -5,8 +5,14 @@ TEST INFRASTRUCTURE ONLY.  Nothing in the product path (the C-ABI library under
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
 legs use it, and only as the checker.
 
-PARITY UNPINNED: the reference repository holds no golden vector, known-answer test
-or call site for the MSM / NTT / quotient path.  The
+PARITY PIN.  Per-function output vectors: none exist — the reference repository holds no
+golden vector, known-answer test or call site for the MSM / NTT / quotient path (SURVEY.md
+F1, F2, section 4), so at that level parity is unpinned and the golden files are generated
+from the definitions.  End to end the oracle IS pinned by the one fixture the reference holds
+for this path, its Solidity verifier: complete SquareCircuit proofs assembled from the oracle's
+functions are accepted by the statement-by-statement transliteration of
+``solidity_verifier_contract/contract.sol`` (``oracle/sol_verifier.py``,
+``tests/test_square_proof_oracle.py``), and tampered ones are rejected.  The
 arithmetic lives in un-vendored git dependencies:
 
   * halo2curves 0.3.1, tag ``0.3.1`` rev 9b67e19b (``Cargo.lock:484-486``):

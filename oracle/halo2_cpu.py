@@ -1,10 +1,12 @@
 """CPU restatement (Python big integers) of the halo2_proofs hot-path functions.
 
-TEST INFRASTRUCTURE ONLY — see the header of ``oracle/bn254.py``.  PARITY UNPINNED:
-the reference never calls any of these, so this file restates the
-*published algorithm* of the pinned dependency and is anchored on mathematical
-uniqueness (a DFT over Fr / a group element of G1) plus the constants the reference
-pins in ``solidity_verifier_contract/contract.sol``.
+TEST INFRASTRUCTURE ONLY — see the header of ``oracle/bn254.py``.  PARITY PIN: no
+upstream output vectors exist (the reference never calls any of these), so
+this file restates the *published algorithm* of the pinned dependency, anchored on
+mathematical uniqueness (a DFT over Fr / a group element of G1) and the constants the
+reference pins in ``solidity_verifier_contract/contract.sol``; end to end it is pinned by
+that contract accepting the proofs built from these functions
+(``tests/test_square_proof_oracle.py``).
 
 Upstream being restated ([DEP] halo2_proofs 0.2.0 @ v2023_01_20, ``Cargo.lock:469-471``):
   * ``halo2_proofs/src/arithmetic.rs``      best_fft, recursive_butterfly_arithmetic,

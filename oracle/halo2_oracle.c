@@ -4,9 +4,12 @@
  * cpu_baseline / --impl reference legs may load this; the product library
  * (anon-aadhaar-halo2_b200/) never links or calls it.
  *
- * PARITY UNPINNED: the reference repository has no call site, test or golden vector for
- * this path and its Rust dependencies cannot be built here
- * (no cargo, no network).  This file restates the published algorithm of
+ * PARITY PIN: per-function output vectors do not exist — the reference repository has no call
+ * site, test or golden vector for this path and its Rust
+ * dependencies cannot be built here (no cargo, no network).  End to end, the commitments this
+ * file's best_multiexp produces are pinned by the reference's Solidity verifier accepting the
+ * proofs that carry them (oracle/sol_verifier.py, tests/test_square_proof_oracle.py).  This file
+ * restates the published algorithm of
  *   [DEP] halo2_proofs 0.2.0 @ v2023_01_20 (reference Cargo.lock:469-471)
  *         src/arithmetic.rs      best_fft, recursive_butterfly_arithmetic,
  *                                best_multiexp, multiexp_serial

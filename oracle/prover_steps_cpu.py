@@ -1,8 +1,11 @@
 """CPU restatement (Python big integers) of the prover loops either side of the MSM / NTT hot
 path (SURVEY.md section 8 f, ranks 1 and 2).
 
-TEST INFRASTRUCTURE ONLY — see the header of ``oracle/bn254.py``.  PARITY UNPINNED (SURVEY F2:
-the reference never runs the prover); each function follows the published algorithm of the pinned
+TEST INFRASTRUCTURE ONLY — see the header of ``oracle/bn254.py``.  PARITY PIN: no upstream output
+vectors exist (the reference never runs the prover); permutation_products,
+eval_polynomial and kate_division are pinned end to end by the reference's verifier contract
+accepting the proofs built from them (tests/test_square_proof_oracle.py), the lookup functions
+only by identities.  Each function follows the published algorithm of the pinned
 dependency ([DEP] halo2_proofs 0.2.0 @ v2023_01_20, reference ``Cargo.lock:469-471``; ff 0.12,
 ``Cargo.lock:339-341``) and is checked against identities that hold for any correct
 implementation (tests/test_prover_steps_oracle.py).

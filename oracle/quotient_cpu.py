@@ -1,8 +1,10 @@
 """CPU restatement (Python big integers) of halo2_proofs' quotient numerator evaluation.
 
-TEST INFRASTRUCTURE ONLY — see the header of ``oracle/bn254.py``.  PARITY UNPINNED for
-the same reason as the rest of the oracle; the one structural pin the reference holds is
-the quotient identity of the SquareCircuit shape in
+TEST INFRASTRUCTURE ONLY — see the header of ``oracle/bn254.py``.  PARITY PIN: no upstream
+output vectors exist; the gate and permutation parts of evaluate_h are pinned end to end by the
+reference's verifier contract accepting the proofs whose h(X) this file computes
+(tests/test_square_proof_oracle.py), the lookup part only by its definition.  The structural
+pin the reference holds is the quotient identity of the SquareCircuit shape in
 ``solidity_verifier_contract/contract.sol:443-505`` (gate ``f_0 * (a_1 - a_0^2)``, the
 ``l_0 / l_last / l_blind`` permutation terms and their y-folding order), which
 ``tests/test_quotient_oracle.py`` checks this restatement against.

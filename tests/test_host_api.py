@@ -36,3 +36,40 @@ def test_length_assertions_mirror_upstream():
         d.lagrange_to_coeff(np.zeros((4, 4), dtype=np.uint64))
     with pytest.raises(AssertionError):
         d.extended_to_coeff(np.zeros((8, 4), dtype=np.uint64))
+
+
+@pytest.mark.gpu
+def test_page_locked_host_buffers(zk):
+    """b200zk_host_register / b200zk_host_alloc: same results from pageable, registered and
+    library-allocated host memory; double registration and foreign pointers are errors."""
+    import ctypes as C
+
+    from oracle import c_oracle as co
+
+    k = 14
+    n = 1 << k
+    s = co.gen_scalars(1, n)
+    g = co.gen_points(2, n)
+    params = zk.ParamsKZG(g, g)
+    want = params.commit(s)
+    d = zk.EvaluationDomain(3, k)
+    want_ntt = s.copy()
+    zk.best_fft(want_ntt, d.omega, k)
+    reg = s.copy()
+    with zk.pinned(reg) as buf:
+        assert np.array_equal(params.commit(buf), want)
+        zk.best_fft(buf, d.omega, k)
+        assert np.array_equal(buf, want_ntt)
+        with pytest.raises(zk.B200zkError, match="already page-locked"):
+            zk.check(zk.load().b200zk_host_register(C.c_void_p(buf.ctypes.data), buf.nbytes))
+    with pytest.raises(zk.B200zkError, match="was not registered"):
+        zk.check(zk.load().b200zk_host_unregister(C.c_void_p(reg.ctypes.data)))
+    own = zk.host_alloc_fr(n)
+    own[:] = s
+    assert np.array_equal(params.commit(own), want)
+    zk.best_fft(own, d.omega, k)
+    assert np.array_equal(own, want_ntt)
+    with pytest.raises(zk.B200zkError, match="not a b200zk_host_alloc"):
+        zk.check(zk.load().b200zk_host_free(C.c_void_p(reg.ctypes.data)))
+    zk.host_free(own)
+    params.close()
