@@ -51,13 +51,14 @@ def test_page_locked_host_buffers(zk):
     s = co.gen_scalars(1, n)
     g = co.gen_points(2, n)
     params = zk.ParamsKZG(g, g)
-    want = params.commit(s)
+    aff = bn.g1_jacobian_limbs_to_affine          # the Jacobian representative depends on the addition order
+    want = aff(params.commit(s))
     d = zk.EvaluationDomain(3, k)
     want_ntt = s.copy()
     zk.best_fft(want_ntt, d.omega, k)
     reg = s.copy()
     with zk.pinned(reg) as buf:
-        assert np.array_equal(params.commit(buf), want)
+        assert aff(params.commit(buf)) == want
         zk.best_fft(buf, d.omega, k)
         assert np.array_equal(buf, want_ntt)
         with pytest.raises(zk.B200zkError, match="already page-locked"):
@@ -66,7 +67,7 @@ def test_page_locked_host_buffers(zk):
         zk.check(zk.load().b200zk_host_unregister(C.c_void_p(reg.ctypes.data)))
     own = zk.host_alloc_fr(n)
     own[:] = s
-    assert np.array_equal(params.commit(own), want)
+    assert aff(params.commit(own)) == want
     zk.best_fft(own, d.omega, k)
     assert np.array_equal(own, want_ntt)
     with pytest.raises(zk.B200zkError, match="not a b200zk_host_alloc"):
