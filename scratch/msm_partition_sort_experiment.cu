@@ -1,0 +1,1244 @@
+// BN254 G1 multi-scalar multiplication (Pippenger) for sm_100a + its C ABI.
+//
+// Device replacement for halo2_proofs 0.2.0 `arithmetic::best_multiexp` and the two
+// callers `ParamsKZG::commit` / `commit_lagrange` ([DEP] halo2_proofs/src/arithmetic.rs,
+// halo2_proofs/src/poly/kzg/commitment.rs @ v2023_01_20, reference Cargo.lock:469-471).
+// The result is the same group element sum_i coeffs[i] * bases[i]; upstream's unsigned
+// ceil(ln n)-bit windows per rayon chunk are a CPU scheduling choice, not part of the
+// result, and are not reproduced (oracle/ restates them for the CPU baseline).
+//
+// Pipeline (all on the device, one stream):
+//   1. digits     scalar -> canonical (one Montgomery reduction) -> signed c-bit digits;
+//                 histogram of (window, |digit|) keys.  Zero digits are dropped, so
+//                 sparse / small witnesses cost proportionally less.
+//   2. scan       exclusive prefix sum of the histogram -> bucket start offsets.
+//   3. scatter    counting sort of (key, point index | sign) pairs by key.
+//   4. accumulate every thread adds a fixed-length chunk of the sorted pair list into
+//                 an XYZZ accumulator (mixed addition, 8M+2S), writing a bucket when
+//                 its run ends inside the chunk and handing the open last run to the
+//                 next level.  Work per thread is constant whatever the bucket sizes
+//                 are, so skewed scalar distributions (all-equal, 0/1 witnesses) do
+//                 not serialise.  Levels >= 1 repeat this on (key, XYZZ) partials.
+//   5. reduce     per window sum_b b * B_b by segmented running sums, segment partials
+//                 combined by the same keyed reduction (key = window).
+//   6. fold       Horner over the windows with c doublings per step; Jacobian out.
+#include "../../include/b200zk.h"
+#include "common.cuh"
+#include "ec.cuh"
+#include "ntt.cuh"  // ld_fr / st_fr helpers
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace zk {
+
+// Registered bases (ParamsKZG::g / g_lagrange): the points, and optionally the table
+// T[w * n + i] = 2^(c*w) * P_i in affine form, which lets every window share one bucket set
+// (no per-window reduction, no doubling chain at the end).
+struct BaseTable {
+    G1Affine* d = nullptr;
+    size_t n = 0;
+    G1Affine* table = nullptr;
+    uint32_t c = 0, nwin = 0;
+};
+
+void msm_release_bases(Context& c) {
+    for (auto& kv : c.bases) {
+        cudaFree(kv.second->d);
+        if (kv.second->table) cudaFree(kv.second->table);
+        delete kv.second;
+    }
+    c.bases.clear();
+}
+
+// ------------------------------------------------------------------------- helpers
+__device__ __forceinline__ Fq ldg_fq(const Fq* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fq r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+// 64-byte points gathered at random: ask L2 to fetch exactly the two sectors of the point
+// (the default promotion pulls the whole 128-byte line, i.e. the neighbouring point as well).
+__device__ __forceinline__ Fq ldg_fq_64B(const Fq* p) {
+    uint4 a, b;
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(reinterpret_cast<const uint4*>(p) + 1));
+    Fq r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ Fq ld_fq(const Fq* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fq r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fq(Fq* p, const Fq& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ G1Xyzz ld_xyzz(const G1Xyzz* p) {
+    G1Xyzz r;
+    r.x = ld_fq(&p->x); r.y = ld_fq(&p->y); r.zz = ld_fq(&p->zz); r.zzz = ld_fq(&p->zzz);
+    return r;
+}
+__device__ __forceinline__ void st_xyzz(G1Xyzz* p, const G1Xyzz& v) {
+    st_fq(&p->x, v.x); st_fq(&p->y, v.y); st_fq(&p->zz, v.zz); st_fq(&p->zzz, v.zzz);
+}
+
+// Signed c-bit digits of a canonical 254-bit scalar; calls f(window, digit) for every
+// non-zero digit, digit in [-2^(c-1), 2^(c-1)].
+template <class F>
+__device__ __forceinline__ void for_each_digit(const uint32_t* s, uint32_t c, uint32_t nwin, F&& f) {
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t mask = (1u << c) - 1u;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < nwin; ++w) {
+        const uint32_t o = w * c;
+        const uint32_t limb = o >> 5, sh = o & 31u;
+        uint32_t raw = 0;
+        if (limb < 8) {
+            raw = s[limb] >> sh;
+            if (sh + c > 32 && limb + 1 < 8) raw |= s[limb + 1] << (32 - sh);
+        }
+        uint32_t d = (raw & mask) + carry;
+        int32_t sd;
+        if (d > half) { sd = (int32_t)d - (int32_t)(1u << c); carry = 1; }
+        else { sd = (int32_t)d; carry = 0; }
+        if (sd != 0) f(w, sd);
+    }
+}
+
+// ------------------------------------------------------------ 1. digits + histogram
+// Also stores the signed digits window-major (digits[(col * nwin + w) * n + i], 0 = dropped)
+// so that the scatter can run one window at a time: all blocks in flight then touch one
+// window's counters (2^(c-1) * 4 B) and one window's slice of the sorted list (<= n * 4 B),
+// which stay in the 126 MB L2 instead of spraying 4-byte stores over every window at once.
+// blockIdx.y = column of a batch.  key = (col * key_windows + (key_windows > 1 ? w : 0)) * nb
+// + |digit| - 1: with a precomputed table all windows share one bucket set (key_windows = 1).
+__global__ void msm_hist_kernel(const Fr* __restrict__ scalars, size_t scalar_stride, size_t n, uint32_t c,
+                                uint32_t nwin, uint32_t key_windows, uint32_t* __restrict__ hist,
+                                int32_t* __restrict__ digits) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;                     // no early return: the warp votes below need every lane
+    const uint32_t col = blockIdx.y;
+    Fr s = Fr::zero();
+    if (valid) s = ldg_fr(scalars + (size_t)col * scalar_stride + i).from_mont();
+    const uint32_t nb = 1u << (c - 1);
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t mask = (1u << c) - 1u;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < nwin; ++w) {
+        const uint32_t o = w * c;
+        const uint32_t limb = o >> 5, sh = o & 31u;
+        uint32_t raw = 0;
+        if (limb < 8) {
+            raw = s.l[limb] >> sh;
+            if (sh + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh);
+        }
+        const uint32_t d = (raw & mask) + carry;
+        int32_t sd;
+        if (d > half) { sd = (int32_t)d - (int32_t)(1u << c); carry = 1; }
+        else { sd = (int32_t)d; carry = 0; }
+        if (valid && digits) digits[((size_t)col * nwin + w) * n + i] = sd;
+        // One atomic per distinct key in the warp: witness columns are full of repeated values
+        // (all-equal scalars put every point of a window in one bucket), and same-address
+        // atomics serialise.
+        const uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
+        const uint32_t key = (valid && sd != 0) ? mag - 1 : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (key != 0xffffffffu && lane == (uint32_t)(__ffs(peers) - 1)) {
+            const size_t group = (size_t)col * key_windows + (key_windows > 1 ? w : 0);
+            atomicAdd(hist + group * nb + key, (uint32_t)__popc(peers));
+        }
+    }
+}
+
+// ------------------------------------------------------------------- 2. prefix scan
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = (lane < blockDim.x / 32) ? warp_sums[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= (uint32_t)o) s += y;
+        }
+        warp_sums[lane] = s;  // inclusive
+    }
+    __syncthreads();
+    const uint32_t base = wid ? warp_sums[wid - 1] : 0u;
+    total = warp_sums[blockDim.x / 32 - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                  uint32_t* __restrict__ bsum, size_t n) {
+    __shared__ uint32_t warp_sums[32];
+    const size_t base = (size_t)blockIdx.x * SCAN_BLOCK + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        t += v[i];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(t, warp_sums, total);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint32_t* bsum, uint32_t nblocks, uint32_t* total_out) {
+    __shared__ uint32_t warp_sums[32];
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < nblocks; base += SCAN_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = (i < nblocks) ? bsum[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, warp_sums, total);
+        if (i < nblocks) bsum[i] = running + ex;
+        running += total;
+    }
+    if (threadIdx.x == 0) *total_out = running;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __restrict__ out, uint32_t* __restrict__ copy,
+                                                                const uint32_t* __restrict__ bsum, size_t n,
+                                                                const uint32_t* __restrict__ total) {
+    const size_t base = (size_t)blockIdx.x * SCAN_BLOCK + (size_t)threadIdx.x * SCAN_ITEMS;
+    const uint32_t add = bsum[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) {
+            const uint32_t v = out[base + i] + add;
+            out[base + i] = v;
+            copy[base + i] = v;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;  // start[K] = number of pairs
+}
+
+// --------------------------------------------------------------------- 3. scatter
+// grid = (ceil(n / 256), columns * windows * nsub): blocks of one (window, bucket sub-range)
+// are scheduled together; the digits are re-read nsub times, streaming.  The 4-byte stores
+// land at random places of the sorted list (ncu at k = 24: 9.8 GB of DRAM traffic for 1.6 GB
+// of algorithmic bytes: every store is a sector read-modify-write); restricting a pass to a
+// bucket sub-range narrows the set of lines being written.
+// The stored value is the index of the point to add: i, or w * table_stride + i into the
+// precomputed table, with the sign of the digit in bit 31.
+__global__ void msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n, uint32_t c, uint32_t nwin,
+                                   uint32_t key_windows, uint32_t table_stride, uint32_t sub_bits,
+                                   uint32_t index_offset, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cw = blockIdx.y >> sub_bits;             // col * nwin + w
+    const uint32_t sub = blockIdx.y & ((1u << sub_bits) - 1u);
+    const uint32_t lane = threadIdx.x & 31u;
+    const int32_t d = (i < n) ? __ldcs(digits + (size_t)cw * n + i) : 0;
+    const uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+    const bool mine = d != 0 && ((mag - 1) >> (c - 1 - sub_bits)) == sub;
+    // warp-aggregated cursor bump: one atomic per distinct bucket in the warp
+    const uint32_t key = mine ? mag - 1 : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+    const uint32_t col = cw / nwin, w = cw - col * nwin;
+    const uint32_t nb = 1u << (c - 1);
+    const size_t group = (size_t)col * key_windows + (key_windows > 1 ? w : 0);
+    uint32_t base = 0;
+    if (mine && lane == leader) base = atomicAdd(cursor + group * nb + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!mine) return;
+    const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    sorted[pos] = ((uint32_t)i + index_offset + w * table_stride) | (d < 0 ? 0x80000000u : 0u);
+}
+
+// ------------------------------------------------------- 3'. two-level partition sort
+// The large-MSM replacement for hist + scan + scatter above.  The atomic scatter writes every
+// 4-byte entry at a random place of the sorted list (a DRAM sector read-modify-write each) and
+// bumps one L2 counter per pair.  Here the pairs are first partitioned into NB <= 1024 coarse
+// bins of 2^F consecutive bucket keys through a shared-memory staging tile, so global writes
+// are runs of consecutive 8-byte (key, value) pairs; then one CTA per coarse bin counts, scans
+// and scatters its bin with shared-memory counters, the 4-byte stores landing inside the bin's
+// own (L2-resident) slice of the sorted list.  Digits never go to memory.
+//   count      per tile: coarse histogram in shared memory -> coarse_hist (one padded counter per bin)
+//   scan       cstart[b] = exclusive prefix, cursor[b] = cstart[b], start[nkeys] = total
+//   partition  per tile: count, reserve [cursor[b], +cnt) per bin, stage pairs by bin, write runs
+//   bin sort   per bin: fine histogram -> start[key], then sorted[start[key]++] = value
+constexpr uint32_t PART_THREADS = 256;
+constexpr uint32_t PART_TILE_PAIRS = 12288;      // 96 KiB of staged pairs per CTA
+constexpr uint32_t PART_MAX_BINS = 1024;
+constexpr uint32_t PART_PAD = 32;                // one coarse counter per 128-byte line
+
+struct PartGeom {
+    uint32_t c, nwin, key_windows, fine_bits, nbins, pts_per_thread;
+    size_t n, scalar_stride;
+};
+
+// calls f(key, value) for every non-zero digit of point i of column col
+template <class F>
+__device__ __forceinline__ void part_point_pairs(const Fr* __restrict__ scalars, const PartGeom& g, uint32_t col, size_t i,
+                                                 uint32_t table_stride, uint32_t index_offset, F&& f) {
+    const Fr s = ldg_fr(scalars + (size_t)col * g.scalar_stride + i).from_mont();
+    const uint32_t nb = 1u << (g.c - 1);
+    for_each_digit(s.l, g.c, g.nwin, [&](uint32_t w, int32_t sd) {
+        const uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
+        const uint32_t group = col * g.key_windows + (g.key_windows > 1 ? w : 0u);
+        const uint32_t key = group * nb + mag - 1u;
+        const uint32_t value = ((uint32_t)i + index_offset + w * table_stride) | (sd < 0 ? 0x80000000u : 0u);
+        f(key, value);
+    });
+}
+
+// cursor of coarse bin b = start of its first bucket (the fine prefix sums are known already)
+__global__ void msm_part_cursor_kernel(const uint32_t* __restrict__ start, uint32_t nbins, uint32_t fine_bits,
+                                       uint32_t* __restrict__ cursor) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbins) cursor[(size_t)b * PART_PAD] = start[(size_t)b << fine_bits];
+}
+
+__global__ void __launch_bounds__(PART_THREADS) msm_partition_kernel(const Fr* __restrict__ scalars, PartGeom g,
+                                                                    uint32_t table_stride, uint32_t index_offset,
+                                                                    uint32_t* __restrict__ cursor,
+                                                                    unsigned long long* __restrict__ pairs) {
+    extern __shared__ __align__(16) unsigned char part_smem[];
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(part_smem);            // per bin: count, then placement rank
+    uint32_t* off = cnt + PART_MAX_BINS;                               // per bin: offset inside the staging tile
+    uint32_t* gbase = off + PART_MAX_BINS;                             // per bin: reserved global position
+    unsigned long long* stage = reinterpret_cast<unsigned long long*>(gbase + PART_MAX_BINS);
+    __shared__ uint32_t warp_sums[32];
+    for (uint32_t b = threadIdx.x; b < PART_MAX_BINS; b += PART_THREADS) cnt[b] = 0;
+    __syncthreads();
+    const uint32_t col = blockIdx.y;
+    const size_t tile_base = (size_t)blockIdx.x * PART_THREADS * g.pts_per_thread;
+    for (uint32_t j = 0; j < g.pts_per_thread; ++j) {
+        const size_t i = tile_base + (size_t)j * PART_THREADS + threadIdx.x;
+        if (i < g.n)
+            part_point_pairs(scalars, g, col, i, 0, 0, [&](uint32_t key, uint32_t) { atomicAdd(&cnt[key >> g.fine_bits], 1u); });
+    }
+    __syncthreads();
+    // exclusive scan of the PART_MAX_BINS counters: 4 consecutive bins per thread
+    constexpr uint32_t PER = PART_MAX_BINS / PART_THREADS;
+    uint32_t v[PER], t = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < PER; ++q) { v[q] = cnt[threadIdx.x * PER + q]; t += v[q]; }
+    uint32_t tile_total;
+    uint32_t ex = block_exclusive_scan(t, warp_sums, tile_total);
+#pragma unroll
+    for (uint32_t q = 0; q < PER; ++q) {
+        const uint32_t b = threadIdx.x * PER + q;
+        off[b] = ex;
+        ex += v[q];
+        gbase[b] = v[q] ? atomicAdd(cursor + (size_t)b * PART_PAD, v[q]) : 0u;
+        cnt[b] = 0;
+    }
+    __syncthreads();
+    for (uint32_t j = 0; j < g.pts_per_thread; ++j) {
+        const size_t i = tile_base + (size_t)j * PART_THREADS + threadIdx.x;
+        if (i < g.n)
+            part_point_pairs(scalars, g, col, i, table_stride, index_offset, [&](uint32_t key, uint32_t value) {
+                const uint32_t b = key >> g.fine_bits;
+                const uint32_t slot = off[b] + atomicAdd(&cnt[b], 1u);
+                stage[slot] = ((unsigned long long)key << 32) | value;
+            });
+    }
+    __syncthreads();
+    for (uint32_t slot = threadIdx.x; slot < tile_total; slot += PART_THREADS) {
+        const unsigned long long pr = stage[slot];
+        const uint32_t b = (uint32_t)(pr >> 32) >> g.fine_bits;
+        pairs[(size_t)gbase[b] + (slot - off[b])] = pr;
+    }
+}
+
+// The partitioned pair list is ordered by coarse bin, so CTAs scheduled together write into a
+// narrow band of the sorted list and bump a narrow band of bucket cursors: both stay in L2.
+constexpr uint32_t ORD_THREADS = 256;
+constexpr uint32_t ORD_PER_THREAD = 4;
+__global__ void __launch_bounds__(ORD_THREADS) msm_ordered_scatter_kernel(const unsigned long long* __restrict__ pairs,
+                                                                         uint32_t npairs_bound, const uint32_t* __restrict__ total,
+                                                                         uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+    const uint32_t npairs = min(npairs_bound, *total);
+    const uint32_t base = blockIdx.x * (ORD_THREADS * ORD_PER_THREAD);
+    if (base >= npairs) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long pr[ORD_PER_THREAD];
+#pragma unroll
+    for (uint32_t u = 0; u < ORD_PER_THREAD; ++u) {
+        const uint32_t p = base + u * ORD_THREADS + threadIdx.x;
+        pr[u] = p < npairs ? __ldcs(pairs + p) : ~0ull;
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < ORD_PER_THREAD; ++u) {
+        const uint32_t key = (uint32_t)(pr[u] >> 32);             // 0xffffffff for padding lanes
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+        uint32_t pos = 0;
+        if (key != 0xffffffffu && lane == leader) pos = atomicAdd(cursor + key, (uint32_t)__popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (key != 0xffffffffu) sorted[pos + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)pr[u];
+    }
+}
+
+constexpr uint32_t MSM_PAD_KEY = 0xffffffffu;   // padding lane (real keys are < 2^31)
+
+// ------------------------------------------------------- 4. bucket accumulation, level 0
+// start[0..K] are the bucket offsets (start[K] = npairs).  Thread t owns pairs
+// [t*L, (t+1)*L).  A run that ends inside the chunk is complete on its right side and is
+// stored to buckets[key] (each key has exactly one such writer per level; buckets were
+// cleared to the identity).  The last run of the chunk is always handed up as
+// (carry_key[t], carry_pt[t]).
+__device__ __forceinline__ uint32_t find_key(const uint32_t* __restrict__ start, uint32_t nkeys, uint32_t pos) {
+    // largest key with start[key] <= pos  (start[key+1] > pos)
+    uint32_t lo = 0, hi = nkeys;  // invariant: start[lo] <= pos < start[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(start + mid) <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ADD = false: buckets were cleared, a closed run is stored.  ADD = true (a later point range of the
+// same MSM, b200zk_msm_g1_registered's upload pipeline): a run that closes inside the chunk
+// continues from what the earlier ranges left in the bucket.
+template <bool ADD>
+__global__ void __launch_bounds__(128, 5) msm_accum_kernel(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                        const uint32_t* __restrict__ start, uint32_t nkeys, uint32_t npairs,
+                                                        uint32_t L, G1Xyzz* __restrict__ buckets,
+                                                        uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt,
+                                                        uint32_t nthreads) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    const uint32_t begin = t * L;
+    const uint32_t end = min(begin + L, npairs);
+    uint32_t key = find_key(start, nkeys, begin);
+    uint32_t run_end = __ldg(start + key + 1);
+    // ADD: the thread that will close a run (the only level-0 writer of that bucket) starts from
+    // what the earlier point ranges left there, so the hot loop carries no extra addition
+    G1Xyzz acc = (ADD && run_end <= end) ? ld_xyzz(buckets + key) : G1Xyzz::identity();
+    // software prefetch of the next point
+    uint32_t e = __ldg(sorted + begin);
+    G1Affine nxt;
+    nxt.x = ldg_fq_64B(&bases[e & 0x7fffffffu].x);
+    nxt.y = ldg_fq_64B(&bases[e & 0x7fffffffu].y);
+#pragma unroll 1
+    for (uint32_t pos = begin; pos < end; ++pos) {
+        G1Affine p = nxt;
+        const bool negate = (e >> 31) != 0;
+        if (pos + 1 < end) {
+            e = __ldg(sorted + pos + 1);
+            nxt.x = ldg_fq_64B(&bases[e & 0x7fffffffu].x);
+            nxt.y = ldg_fq_64B(&bases[e & 0x7fffffffu].y);
+        }
+        if (pos >= run_end) {
+            st_xyzz(buckets + key, acc);
+            do {
+                ++key;
+                run_end = __ldg(start + key + 1);
+            } while (pos >= run_end);
+            acc = (ADD && run_end <= end) ? ld_xyzz(buckets + key) : G1Xyzz::identity();
+        }
+        if (negate) p.y = p.y.neg();
+        acc.add_affine(p);
+    }
+    if (run_end == end) {
+        // the chunk ends exactly where its last run ends: nothing continues into the next
+        // chunk, so the run is complete on its right side like the interior ones
+        st_xyzz(buckets + key, acc);
+        acc = G1Xyzz::identity();   // hand up (key, identity): keys stay dense and sorted
+    }
+    carry_key[t] = key;
+    st_xyzz(carry_pt + t, acc);
+}
+
+// ------------------------------------------------------ 4b. keyed reduction, level >= 1
+// Entries (keys[i], pts[i]) with non-decreasing keys.  A run of equal keys is *closed* where
+// it ends (the next entry has another key, or there is none); exactly one thread per level
+// sees a given key close, and only that thread adds the run's sum into buckets[key].  Open
+// last runs are handed up as (key, partial); closed ones hand up (key, identity) so the next
+// level's keys stay dense and sorted.
+//
+// Sequential form (throughput regime): thread t owns entries [t*L, (t+1)*L).
+__global__ void __launch_bounds__(128) msm_combine_kernel(const uint32_t* __restrict__ keys, const G1Xyzz* __restrict__ pts,
+                                                          uint32_t count, uint32_t L, G1Xyzz* __restrict__ buckets,
+                                                          uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt,
+                                                          uint32_t nthreads) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    const uint32_t begin = t * L;
+    const uint32_t end = min(begin + L, count);
+    uint32_t key = keys[begin];
+    G1Xyzz acc = G1Xyzz::identity();
+    auto flush = [&]() {
+        if (!acc.is_identity()) {
+            G1Xyzz b = ld_xyzz(buckets + key);
+            b.add(acc);
+            st_xyzz(buckets + key, b);
+        }
+    };
+#pragma unroll 1
+    for (uint32_t i = begin; i < end; ++i) {
+        const uint32_t k = keys[i];
+        if (k != key) {
+            flush();
+            acc = G1Xyzz::identity();
+            key = k;
+        }
+        G1Xyzz p = ld_xyzz(pts + i);
+        acc.add(p);
+    }
+    if (end == count || keys[end] != key) {
+        flush();
+        acc = G1Xyzz::identity();
+    }
+    carry_key[t] = key;
+    st_xyzz(carry_pt + t, acc);
+}
+
+__device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& v, uint32_t d) {
+    G1Xyzz r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], d);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], d);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], d);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], d);
+    }
+    return r;
+}
+
+// Warp form (latency regime): one entry per lane, segmented shuffle reduction by key in five
+// steps; each warp hands up one entry, so a level shrinks the list 32x for the latency of
+// five point additions.  When count <= 32 the single warp closes everything.
+__global__ void __launch_bounds__(128) msm_combine_warp_kernel(const uint32_t* __restrict__ keys,
+                                                               const G1Xyzz* __restrict__ pts, uint32_t count,
+                                                               G1Xyzz* __restrict__ buckets,
+                                                               uint32_t* __restrict__ carry_key,
+                                                               G1Xyzz* __restrict__ carry_pt) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = gid >> 5;
+    const uint32_t base = warp << 5;
+    if (base >= count) return;                       // whole warp beyond the list
+    const bool valid = gid < count;
+    const uint32_t key = valid ? keys[gid] : MSM_PAD_KEY;
+    G1Xyzz v = valid ? ld_xyzz(pts + gid) : G1Xyzz::identity();
+#pragma unroll 1
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
+        const G1Xyzz o = shfl_down_xyzz(v, d);
+        if (lane + d < 32 && ok == key) v.add(o);
+    }
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (prev != key);
+    const uint32_t last_lane = min(31u, count - base - 1u);
+    const uint32_t k_last = __shfl_sync(0xffffffffu, key, last_lane);
+    if (!(head && valid)) return;
+    const bool reaches_end = (key == k_last);
+    const bool open = reaches_end && (base + 32 < count) && (keys[base + 32] == key);
+    if (open) {
+        carry_key[warp] = key;
+        st_xyzz(carry_pt + warp, v);
+        return;
+    }
+    if (!v.is_identity()) {
+        G1Xyzz b = ld_xyzz(buckets + key);
+        b.add(v);
+        st_xyzz(buckets + key, b);
+    }
+    if (reaches_end) {
+        carry_key[warp] = key;
+        st_xyzz(carry_pt + warp, G1Xyzz::identity());
+    }
+}
+
+// --------------------------------------------------------------- 5. window reduction
+// Thread (w, seg) walks `seglen` buckets of window w from the top: run += B_b,
+// sum += run, then emits  sum + (lo-1) * run  with key w, where lo is the weight of the
+// segment's lowest bucket.  The sum over a window's segments is sum_b b * B_b.
+__global__ void __launch_bounds__(128, 4) msm_reduce_kernel(const G1Xyzz* __restrict__ buckets, uint32_t nb, uint32_t seglen,
+                                                         uint32_t segs_per_win, uint32_t nwin,
+                                                         uint32_t* __restrict__ out_key, G1Xyzz* __restrict__ out_pt) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= segs_per_win * nwin) return;
+    const uint32_t w = t / segs_per_win, seg = t % segs_per_win;
+    const uint32_t lo_idx = seg * seglen;                 // bucket index (weight = index + 1)
+    const uint32_t hi_idx = min(lo_idx + seglen, nb);
+    const G1Xyzz* B = buckets + (size_t)w * nb;
+    G1Xyzz run = G1Xyzz::identity(), sum = G1Xyzz::identity();
+#pragma unroll 1
+    for (uint32_t b = hi_idx; b > lo_idx; --b) {
+        G1Xyzz x = ld_xyzz(B + (b - 1));
+        run.add(x);
+        sum.add(run);
+    }
+    // sum = sum_{b} (b - lo_idx) * B_b  with weights 1..seglen; add lo_idx * run
+    uint32_t k = lo_idx;
+    if (k != 0 && !run.is_identity()) {
+        G1Xyzz acc = G1Xyzz::identity();
+        for (int bit = 31 - __clz(k); bit >= 0; --bit) {
+            acc = acc.dbl();
+            if ((k >> bit) & 1u) acc.add(run);
+        }
+        sum.add(acc);
+    }
+    out_key[t] = w;
+    st_xyzz(out_pt + t, sum);
+}
+
+// ----------------------------------------------------------------------- 6. fold
+// One thread per column of the batch: Horner over that column's windows.
+__global__ void msm_fold_kernel(const G1Xyzz* __restrict__ win, uint32_t nwin, uint32_t c, uint32_t count,
+                                G1Jacobian* out) {
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= count) return;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (int w = (int)nwin - 1; w >= 0; --w) {
+        if (!acc.is_identity())
+            for (uint32_t i = 0; i < c; ++i) acc = acc.dbl();
+        G1Xyzz x = ld_xyzz(win + (size_t)col * nwin + w);
+        acc.add(x);
+    }
+    out[col] = acc.to_jacobian();
+}
+
+// T[w * n + i] = 2^(c*w) * P_i, affine.  One thread per point walks the doubling chain and
+// normalises each multiple with a field inversion (one-off cost at registration).
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const G1Affine* __restrict__ bases, size_t n, uint32_t c,
+                                                             uint32_t nwin, G1Affine* __restrict__ table) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p;
+    p.x = ldg_fq(&bases[i].x);
+    p.y = ldg_fq(&bases[i].y);
+    st_fq(&table[i].x, p.x);
+    st_fq(&table[i].y, p.y);
+    for (uint32_t w = 1; w < nwin; ++w) {
+        if (!p.is_identity()) {
+            G1Xyzz a = G1Xyzz::double_affine(p);
+            for (uint32_t k = 1; k < c; ++k) a = a.dbl();
+            G1Jacobian j = a.to_jacobian_normalized();
+            p.x = j.x;
+            p.y = j.y;
+        }
+        st_fq(&table[(size_t)w * n + i].x, p.x);
+        st_fq(&table[(size_t)w * n + i].y, p.y);
+    }
+}
+
+__global__ void g1_sum_kernel(const G1Jacobian* __restrict__ pts, uint32_t count, G1Jacobian* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t i = 0; i < count; ++i) {
+        G1Jacobian j = pts[i];
+        if (j.z.is_zero()) continue;
+        G1Xyzz p;  // Jacobian (X, Y, Z) -> XYZZ (X, Y, Z^2, Z^3)
+        p.x = j.x; p.y = j.y; p.zz = j.z.sqr(); p.zzz = p.zz * j.z;
+        acc.add(p);
+    }
+    *out = acc.to_jacobian();
+}
+
+// ------------------------------------------------------------------ host pipeline
+// ------------------------------------------------------------- per-stage timing
+// Optional CUDA-event bracketing of the pipeline stages (b200zk_msm_profile), used by
+// bench.py to time the dominant kernel on the stream it runs on.
+enum MsmStage { MSM_ST_HIST = 0, MSM_ST_SCAN, MSM_ST_SCATTER, MSM_ST_SYNC, MSM_ST_ACCUM, MSM_ST_COMBINE,
+                MSM_ST_REDUCE, MSM_ST_REDUCE_COMBINE, MSM_ST_FOLD, MSM_ST_END, MSM_ST_COUNT };
+struct MsmInfo { uint64_t n; uint32_t c, nwin, npairs, chunk; };
+static MsmInfo g_msm_info = {0, 0, 0, 0, 0};
+static bool g_msm_profile = false;
+static uint32_t g_msm_max_chunk = 128;   // tunable (b200zk_msm_tune)
+static uint32_t g_msm_max_seglen = 64;    // measured: 104 -> 64 takes the 242-column reduce from 3.5 to 3.1 ms
+static uint32_t g_msm_force_c = 0;
+// scatter sub-range bits; B200ZK_MSM_SUB_BITS overrides the automatic choice (experiments only)
+// upload pipeline of b200zk_msm_g1_registered (one large host-side commit): number of point
+// ranges and the size from which it is used
+constexpr size_t MSM_MAX_PARTS = 16;
+static size_t g_msm_pipe_parts = getenv("B200ZK_MSM_PIPE_PARTS") ? (size_t)atoi(getenv("B200ZK_MSM_PIPE_PARTS")) : 4;
+static size_t g_msm_pipe_min_n = getenv("B200ZK_MSM_PIPE_MIN_N") ? (size_t)atoll(getenv("B200ZK_MSM_PIPE_MIN_N")) : ((size_t)1 << 22);
+static cudaStream_t g_msm_copy_stream = nullptr;
+static cudaEvent_t g_msm_part_ev[MSM_MAX_PARTS + 1];
+// sort of the (bucket, point) pairs: 0 = by size, 1 = atomic scatter, 2 = two-level partition
+static uint32_t g_msm_sort_mode = getenv("B200ZK_MSM_SORT_MODE") ? (uint32_t)atoi(getenv("B200ZK_MSM_SORT_MODE")) : 0u;
+static size_t g_msm_partition_min_pairs = getenv("B200ZK_MSM_PARTITION_MIN_PAIRS") ? (size_t)atoll(getenv("B200ZK_MSM_PARTITION_MIN_PAIRS")) : ((size_t)1 << 22);
+static uint32_t g_msm_force_sub = getenv("B200ZK_MSM_SUB_BITS") ? (uint32_t)atoi(getenv("B200ZK_MSM_SUB_BITS")) : 0xffffffffu;
+static cudaEvent_t g_msm_ev[MSM_ST_COUNT];
+static bool g_msm_ev_made = false, g_msm_ev_valid[MSM_ST_COUNT];
+static cudaStream_t g_msm_ev_stream = nullptr;
+
+struct StageTimer {
+    cudaStream_t s;
+    bool on;
+    StageTimer(Context&, cudaStream_t st) : s(st), on(g_msm_profile) {
+        if (!on) return;
+        if (!g_msm_ev_made) {
+            for (int i = 0; i < MSM_ST_COUNT; ++i) ZK_CUDA(cudaEventCreate(&g_msm_ev[i]));
+            g_msm_ev_made = true;
+        }
+        for (int i = 0; i < MSM_ST_COUNT; ++i) g_msm_ev_valid[i] = false;
+        g_msm_ev_stream = st;
+    }
+    void mark(int stage) {
+        if (!on) return;
+        ZK_CUDA(cudaEventRecord(g_msm_ev[stage], s));
+        g_msm_ev_valid[stage] = true;
+    }
+};
+
+// minimise 10*n*W (mixed adds) + 30*G*2^(c-1) (two full adds per bucket + slack), where G
+// is the number of bucket sets: W without a precomputed table, 1 with one.
+static uint32_t choose_window(size_t n, bool shared_buckets) {
+    double best = 1e300;
+    uint32_t bc = 4;
+    for (uint32_t c = 4; c <= 23; ++c) {
+        const double W = (255 + c - 1) / c;
+        const double cost = 10.0 * (double)n * W + 30.0 * (shared_buckets ? 1.0 : W) * (double)(1u << (c - 1));
+        if (cost < best) { best = cost; bc = c; }
+    }
+    return bc;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct MsmPre {
+    const G1Affine* table;
+    size_t n_reg;
+    uint32_t c, nwin;
+};
+
+// Launch the keyed-reduction levels on (keys, pts)[count] until everything has been
+// added into `buckets`.  Small inputs use short chunks: the cost of a level is the latency
+// of L dependent point additions, not throughput.
+static void run_combine_levels(Context& c, uint32_t* keysA, G1Xyzz* ptsA, uint32_t* keysB, G1Xyzz* ptsB,
+                               uint32_t count, G1Xyzz* buckets, cudaStream_t s) {
+    while (count > 0) {
+        if (count > 32768u) {
+            // throughput regime: sequential chunks, one addition per entry
+            const uint32_t L = count > (uint32_t)c.sm_count * 4096u ? 16u : 4u;
+            const uint32_t nthreads = (count + L - 1) / L;
+            msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, count, L, buckets, keysB, ptsB,
+                                                                      nthreads);
+            ZK_LAUNCH_CHECK();
+            count = nthreads;
+        } else {
+            const uint32_t nwarps = (count + 31) / 32;
+            msm_combine_warp_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, count, buckets, keysB, ptsB);
+            ZK_LAUNCH_CHECK();
+            if (nwarps == 1) break;
+            count = nwarps;
+        }
+        std::swap(keysA, keysB);
+        std::swap(ptsA, ptsB);
+    }
+}
+
+// Sum `per_group` consecutive partials of each group: grid (nsplit, groups), 256 threads;
+// thread j adds its strided share, then a shared-memory tree.  out[group * nsplit + split].
+__global__ void __launch_bounds__(256) msm_group_sum_kernel(const G1Xyzz* __restrict__ pts, uint32_t per_group,
+                                                            uint32_t nsplit, G1Xyzz* __restrict__ out) {
+    extern __shared__ uint4 gs_smem[];
+    G1Xyzz* sh = reinterpret_cast<G1Xyzz*>(gs_smem);
+    const uint32_t group = blockIdx.y, split = blockIdx.x;
+    const uint32_t span = (per_group + nsplit - 1) / nsplit;
+    const uint32_t lo = split * span, hi = min(lo + span, per_group);
+    const G1Xyzz* base = pts + (size_t)group * per_group;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) {
+        G1Xyzz p = ld_xyzz(base + i);
+        acc.add(p);
+    }
+    st_xyzz(sh + threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t stride = 128; stride > 0; stride >>= 1) {
+        if (threadIdx.x < stride) {
+            G1Xyzz a = ld_xyzz(sh + threadIdx.x);
+            G1Xyzz b = ld_xyzz(sh + threadIdx.x + stride);
+            a.add(b);
+            st_xyzz(sh + threadIdx.x, a);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_xyzz(out + (size_t)group * nsplit + split, ld_xyzz(sh));
+}
+
+// `count` MSMs over the same n bases: column j uses scalars d_scalars + j * scalar_stride and
+// writes d_out[j].  All inputs device-resident.  `pre` (optional) is a per-window table.
+// One MSM may be fed in consecutive point ranges that share the bucket set (a host-side commit
+// whose scalars are still arriving over PCIe): `first` clears the buckets, later parts add into
+// them, `last` runs the bucket reduction.  index_offset = first point of the range.
+struct MsmPart {
+    bool first = true, last = true;
+    uint32_t index_offset = 0;
+};
+
+static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, size_t count,
+                       const G1Affine* d_bases, size_t n, const MsmPre* pre, G1Jacobian* d_out, cudaStream_t s,
+                       const MsmPart& part = MsmPart()) {
+    ZK_REQUIRE(n < ((size_t)1 << 28), "MSM size must be below 2^28 points");
+    if (count == 0) return;
+    if (n == 0) {
+        G1Jacobian id;
+        id.x = Fq::zero(); id.y = Fq::one(); id.z = Fq::zero();
+        for (size_t j = 0; j < count; ++j)
+            ZK_CUDA(cudaMemcpyAsync(d_out + j, &id, sizeof id, cudaMemcpyHostToDevice, s));
+        ZK_CUDA(cudaStreamSynchronize(s));
+        return;
+    }
+    const uint32_t cbits = pre ? pre->c : (g_msm_force_c ? g_msm_force_c : choose_window(n, false));
+    const uint32_t nwin = (255 + cbits - 1) / cbits;
+    const uint32_t key_windows = pre ? 1u : nwin;
+    const uint32_t nb = 1u << (cbits - 1);
+    const size_t groups = count * key_windows;            // bucket sets
+    const size_t nkeys_sz = groups * nb;
+    const size_t max_pairs = n * nwin * count;
+    ZK_REQUIRE(max_pairs < ((size_t)1 << 32) && nkeys_sz < ((size_t)1 << 31), "MSM batch too large for 32-bit offsets");
+    ZK_REQUIRE(count * nwin <= 65535, "MSM batch has too many (column, window) pairs");
+    if (pre) ZK_REQUIRE(pre->n_reg * (size_t)nwin < ((size_t)1 << 31), "precomputed table too large for 31-bit indices");
+    const uint32_t nkeys = (uint32_t)nkeys_sz;
+
+    // ---- carve the sort arena (sizes known up front)
+    const uint32_t scan_blocks = (uint32_t)((nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    // segment length of the bucket reduction: enough segments to fill the machine, short
+    // enough that 2 * seglen dependent additions stay cheap
+    uint32_t seglen = (uint32_t)std::min<uint64_t>(g_msm_max_seglen, std::max<uint64_t>(4, nkeys / ((uint64_t)c.sm_count * 256)));
+    if (seglen > nb) seglen = nb;
+    const uint32_t segs_per_group = (nb + seglen - 1) / seglen;
+    const size_t red_entries = (size_t)segs_per_group * groups;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_buckets = carve((size_t)nkeys * sizeof(G1Xyzz));   // first: same place for every part of an MSM
+    const size_t o_win = carve(groups * sizeof(G1Xyzz));
+    // sort method: two-level partition for large pair lists, atomic scatter otherwise
+    uint32_t key_bits = 0;
+    while (((size_t)1 << key_bits) < nkeys_sz) ++key_bits;
+    const uint32_t fine_bits = key_bits > 9 ? key_bits - 9 : 0;
+    const uint32_t nbins = (uint32_t)((nkeys_sz + ((size_t)1 << fine_bits) - 1) >> fine_bits);
+    const bool part_ok = nbins <= PART_MAX_BINS && PART_THREADS * nwin <= PART_TILE_PAIRS;
+    const bool use_partition = part_ok && (g_msm_sort_mode == 2 || (g_msm_sort_mode == 0 && max_pairs >= g_msm_partition_min_pairs));
+    const size_t o_hist = carve(((size_t)nkeys + 1) * 4);
+    const size_t o_start = carve(((size_t)nkeys + 1) * 4);
+    const size_t o_cursor = carve(((size_t)nkeys + 1) * 4);
+    const size_t o_bsum = carve(((size_t)scan_blocks + 1) * 4);
+    const size_t o_coarse = carve((size_t)PART_MAX_BINS * PART_PAD * 4);
+    const size_t o_total = carve(256);
+    const size_t o_sorted = carve(max_pairs * 4);
+    const size_t o_digits = carve(max_pairs * (use_partition ? 8 : 4));
+    char* base = (char*)c.msm_work.get(off);
+    uint32_t* hist = (uint32_t*)(base + o_hist);
+    uint32_t* start = (uint32_t*)(base + o_start);
+    uint32_t* cursor = (uint32_t*)(base + o_cursor);
+    uint32_t* bsum = (uint32_t*)(base + o_bsum);
+    uint32_t* total = (uint32_t*)(base + o_total);
+    uint32_t* sorted = (uint32_t*)(base + o_sorted);
+    int32_t* digits = (int32_t*)(base + o_digits);
+    G1Xyzz* buckets = (G1Xyzz*)(base + o_buckets);
+    G1Xyzz* win = (G1Xyzz*)(base + o_win);
+
+    StageTimer T(c, s);
+    // ---- 1-3: sort (bucket, point) pairs
+    if (part.first) {
+        ZK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nkeys * sizeof(G1Xyzz), s));
+        ZK_CUDA(cudaMemsetAsync(win, 0, groups * sizeof(G1Xyzz), s));
+    }
+    if (use_partition) {
+        // fine histogram (no digits stored) -> bucket offsets; partition by coarse bin; ordered scatter
+        PartGeom g;
+        g.c = cbits; g.nwin = nwin; g.key_windows = key_windows; g.fine_bits = fine_bits; g.nbins = nbins;
+        g.pts_per_thread = std::max<uint32_t>(1, PART_TILE_PAIRS / (PART_THREADS * nwin));
+        g.n = n; g.scalar_stride = scalar_stride;
+        const unsigned tiles = (unsigned)((n + (size_t)PART_THREADS * g.pts_per_thread - 1) / ((size_t)PART_THREADS * g.pts_per_thread));
+        unsigned long long* pairs = (unsigned long long*)digits;
+        uint32_t* coarse_cursor = (uint32_t*)(base + o_coarse);
+        ZK_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nkeys + 1) * 4, s));
+        const unsigned sblocks = (unsigned)((n + 255) / 256);
+        T.mark(MSM_ST_HIST);
+        msm_hist_kernel<<<dim3(sblocks, (unsigned)count), 256, 0, s>>>(d_scalars, scalar_stride, n, cbits, nwin,
+                                                                        key_windows, hist, nullptr);
+        ZK_LAUNCH_CHECK();
+        T.mark(MSM_ST_SCAN);
+        scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(hist, start, bsum, nkeys);
+        ZK_LAUNCH_CHECK();
+        scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(bsum, scan_blocks, total);
+        ZK_LAUNCH_CHECK();
+        scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, nkeys, total);
+        ZK_LAUNCH_CHECK();
+        msm_part_cursor_kernel<<<(nbins + 255) / 256, 256, 0, s>>>(start, nbins, fine_bits, coarse_cursor);
+        ZK_LAUNCH_CHECK();
+        T.mark(MSM_ST_SCATTER);
+        const size_t part_smem = 3 * PART_MAX_BINS * 4 + (size_t)PART_TILE_PAIRS * 8;
+        static bool attr_set = false;
+        if (!attr_set) {
+            ZK_CUDA(cudaFuncSetAttribute(msm_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+            attr_set = true;
+        }
+        msm_partition_kernel<<<dim3(tiles, (unsigned)count), PART_THREADS, part_smem, s>>>(
+            d_scalars, g, pre ? (uint32_t)pre->n_reg : 0u, part.index_offset, coarse_cursor, pairs);
+        ZK_LAUNCH_CHECK();
+        const uint32_t ord_blocks = (uint32_t)((max_pairs + ORD_THREADS * ORD_PER_THREAD - 1) / (ORD_THREADS * ORD_PER_THREAD));
+        msm_ordered_scatter_kernel<<<ord_blocks, ORD_THREADS, 0, s>>>(pairs, (uint32_t)std::min<size_t>(max_pairs, 0xffffffffu), total, cursor, sorted);
+        ZK_LAUNCH_CHECK();
+    } else {
+    ZK_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nkeys + 1) * 4, s));
+    const unsigned sblocks = (unsigned)((n + 255) / 256);
+    T.mark(MSM_ST_HIST);
+    msm_hist_kernel<<<dim3(sblocks, (unsigned)count), 256, 0, s>>>(d_scalars, scalar_stride, n, cbits, nwin,
+                                                                    key_windows, hist, digits);
+    ZK_LAUNCH_CHECK();
+    T.mark(MSM_ST_SCAN);
+    scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(hist, start, bsum, nkeys);
+    ZK_LAUNCH_CHECK();
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(bsum, scan_blocks, total);
+    ZK_LAUNCH_CHECK();
+    scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, nkeys, total);
+    ZK_LAUNCH_CHECK();
+    T.mark(MSM_ST_SCATTER);
+    // bucket sub-ranges: measured on B200 at k = 24, one split helps the shared-bucket (table)
+    // layout (6.4 -> 5.5 ms) and none helps the per-window layout
+    uint32_t sub_bits = (pre && n * 4 > ((size_t)16 << 20) && cbits > 2 && count * nwin * 2 <= 65535) ? 1u : 0u;
+    if (g_msm_force_sub != 0xffffffffu) sub_bits = std::min<uint32_t>(g_msm_force_sub, cbits - 1);
+    msm_scatter_kernel<<<dim3(sblocks, (unsigned)((count * nwin) << sub_bits)), 256, 0, s>>>(
+        digits, n, cbits, nwin, key_windows, pre ? (uint32_t)pre->n_reg : 0u, sub_bits, part.index_offset, cursor, sorted);
+    ZK_LAUNCH_CHECK();
+    }
+    T.mark(MSM_ST_SYNC);
+    uint32_t npairs = 0;
+    ZK_CUDA(cudaMemcpyAsync(&npairs, total, 4, cudaMemcpyDeviceToHost, s));
+    ZK_CUDA(cudaStreamSynchronize(s));
+
+    // chunk length: keep >= ~4096 threads per SM queued, between 4 and 128 pairs each (longer
+    // chunks mean fewer open runs handed to the keyed-reduction levels)
+    const uint32_t L = (uint32_t)std::min<uint64_t>(g_msm_max_chunk, std::max<uint64_t>(4, npairs / ((uint64_t)c.sm_count * 4096)));
+    const uint32_t nthreads0 = (npairs + L - 1) / L;
+    // ---- carve the carry arena now that the pair count is known
+    const size_t carry_cap = std::max<size_t>(std::max<size_t>(nthreads0, red_entries), 64);
+    off = 0;
+    const size_t o_keyA = carve(carry_cap * 4);
+    const size_t o_ptA = carve(carry_cap * sizeof(G1Xyzz));
+    const size_t capB = std::max<size_t>(carry_cap / 4 + 64, groups * 64);
+    const size_t o_keyB = carve(capB * 4);
+    const size_t o_ptB = carve(capB * sizeof(G1Xyzz));
+    char* cbase = (char*)c.msm_carry.get(off);
+    uint32_t* keyA = (uint32_t*)(cbase + o_keyA);
+    G1Xyzz* ptA = (G1Xyzz*)(cbase + o_ptA);
+    uint32_t* keyB = (uint32_t*)(cbase + o_keyB);
+    G1Xyzz* ptB = (G1Xyzz*)(cbase + o_ptB);
+    g_msm_info.n = n * count; g_msm_info.c = cbits; g_msm_info.nwin = nwin; g_msm_info.npairs = npairs; g_msm_info.chunk = L;
+
+    // ---- 4: accumulate
+    T.mark(MSM_ST_ACCUM);
+    if (npairs > 0) {
+        if (part.first)
+            msm_accum_kernel<false><<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start,
+                                                                            nkeys, npairs, L, buckets, keyA, ptA, nthreads0);
+        else
+            msm_accum_kernel<true><<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start,
+                                                                           nkeys, npairs, L, buckets, keyA, ptA, nthreads0);
+        ZK_LAUNCH_CHECK();
+        T.mark(MSM_ST_COMBINE);
+        run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, buckets, s);
+    }
+
+    if (!part.last) {
+        T.mark(MSM_ST_END);
+        return;
+    }
+    // ---- 5: per-bucket-set running sums, then keyed reduction with key = bucket set
+    T.mark(MSM_ST_REDUCE);
+    {
+        const uint32_t nthreads = (uint32_t)red_entries;
+        msm_reduce_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(buckets, nb, seglen, segs_per_group, (uint32_t)groups,
+                                                                 keyA, ptA);
+        ZK_LAUNCH_CHECK();
+        T.mark(MSM_ST_REDUCE_COMBINE);
+        // per bucket set: sum its segment partials (block tree, two stages when long)
+        const uint32_t nsplit = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, segs_per_group / 2048));
+        const int smem = 256 * sizeof(G1Xyzz);
+        if (nsplit == 1) {
+            msm_group_sum_kernel<<<dim3(1, (unsigned)groups), 256, smem, s>>>(ptA, segs_per_group, 1, win);
+            ZK_LAUNCH_CHECK();
+        } else {
+            msm_group_sum_kernel<<<dim3(nsplit, (unsigned)groups), 256, smem, s>>>(ptA, segs_per_group, nsplit, ptB);
+            ZK_LAUNCH_CHECK();
+            msm_group_sum_kernel<<<dim3(1, (unsigned)groups), 256, smem, s>>>(ptB, nsplit, 1, win);
+            ZK_LAUNCH_CHECK();
+        }
+    }
+    T.mark(MSM_ST_FOLD);
+    // ---- 6: fold each column's windows (a single one with a precomputed table)
+    msm_fold_kernel<<<(unsigned)((count + 31) / 32), 32, 0, s>>>(win, key_windows, cbits, (uint32_t)count, d_out);
+    ZK_LAUNCH_CHECK();
+    T.mark(MSM_ST_END);
+}
+
+static void copy_point_out(Context& c, const G1Jacobian* d, uint64_t* out, cudaStream_t s) {
+    ZK_CUDA(cudaMemcpyAsync(out, d, sizeof(G1Jacobian), cudaMemcpyDeviceToHost, s));
+    ZK_CUDA(cudaStreamSynchronize(s));
+    (void)c;
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+extern "C" {
+
+int b200zk_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_xyz[12]) {
+    return guarded([&] {
+        ZK_REQUIRE(out_xyz && (n == 0 || (scalars && bases)), "null argument");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = c.stream;
+        Fr* ds = (Fr*)c.msm_scalars.get(std::max<size_t>(n, 1) * sizeof(Fr));
+        G1Affine* db = (G1Affine*)c.msm_bases.get(std::max<size_t>(n, 1) * sizeof(G1Affine));
+        G1Jacobian* dout = (G1Jacobian*)c.misc.get(sizeof(G1Jacobian));
+        if (n) {
+            ZK_CUDA(cudaMemcpyAsync(ds, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            ZK_CUDA(cudaMemcpyAsync(db, bases, n * sizeof(G1Affine), cudaMemcpyHostToDevice, s));
+        }
+        msm_device(c, ds, n, 1, db, n, nullptr, dout, s);
+        copy_point_out(c, dout, out_xyz, s);
+    });
+}
+
+static void register_bases(const uint64_t* bases, size_t n, int precompute, uint64_t* handle_out) {
+    ZK_REQUIRE(handle_out && (n == 0 || bases), "null argument");
+    ensure_init();
+    Context& c = ctx();
+    BaseTable* t = new BaseTable();
+    t->n = n;
+    if (n) {
+        ZK_CUDA(cudaMalloc(&t->d, n * sizeof(G1Affine)));
+        ZK_CUDA(cudaMemcpy(t->d, bases, n * sizeof(G1Affine), cudaMemcpyHostToDevice));
+    }
+    if (n && precompute) {
+        t->c = choose_window(n, true);
+        t->nwin = (255 + t->c - 1) / t->c;
+        const size_t bytes = n * (size_t)t->nwin * sizeof(G1Affine);
+        size_t free_b = 0, total_b = 0;
+        ZK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (n * (size_t)t->nwin < ((size_t)1 << 31) && bytes < free_b / 2) {
+            ZK_CUDA(cudaMalloc(&t->table, bytes));
+            msm_precompute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(t->d, n, t->c, t->nwin, t->table);
+            ZK_LAUNCH_CHECK();
+            ZK_CUDA(cudaStreamSynchronize(c.stream));
+        }  // otherwise: plain registered bases (generic pipeline)
+    }
+    const uint64_t h = c.next_handle++;
+    c.bases[h] = t;
+    *handle_out = h;
+}
+
+int b200zk_bases_register(const uint64_t* bases, size_t n, uint64_t* handle_out) {
+    return guarded([&] { register_bases(bases, n, 1, handle_out); });
+}
+
+int b200zk_bases_register_ex(const uint64_t* bases, size_t n, int precompute_windows, uint64_t* handle_out) {
+    return guarded([&] { register_bases(bases, n, precompute_windows, handle_out); });
+}
+
+int b200zk_bases_evict(uint64_t handle) {
+    return guarded([&] {
+        Context& c = ctx();
+        auto it = c.bases.find(handle);
+        ZK_REQUIRE(it != c.bases.end(), "unknown bases handle");
+        if (c.ready) {
+            cudaSetDevice(c.device);
+            cudaStreamSynchronize(c.stream);
+        }
+        cudaFree(it->second->d);
+        if (it->second->table) cudaFree(it->second->table);
+        delete it->second;
+        c.bases.erase(it);
+    });
+}
+
+static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stride, size_t count, size_t n,
+                           uint64_t* out_xyz) {
+    ZK_REQUIRE(out_xyz && (n == 0 || scalars), "null argument");
+    ZK_REQUIRE(count <= 1 || stride >= n, "batch stride smaller than the column");
+    ensure_init();
+    Context& c = ctx();
+    auto it = c.bases.find(handle);
+    ZK_REQUIRE(it != c.bases.end(), "unknown bases handle");
+    BaseTable* t = it->second;
+    ZK_REQUIRE(n <= t->n, "more scalars than registered bases");
+    if (count == 0) return;
+    cudaStream_t s = c.stream;
+    Fr* ds = (Fr*)c.msm_scalars.get(std::max<size_t>(n * count, 1) * sizeof(Fr));
+    G1Jacobian* dout = (G1Jacobian*)c.misc.get(count * sizeof(G1Jacobian));
+    MsmPre pre{t->table, t->n, t->c, t->nwin};
+    // One large commit with a window table: feed it in point ranges that share the bucket set,
+    // so the upload of range p+1 runs under the sort + accumulation of range p.
+    const size_t parts = (count == 1 && t->table && n >= g_msm_pipe_min_n) ? std::min<size_t>(g_msm_pipe_parts, MSM_MAX_PARTS) : 1;
+    if (parts > 1) {
+        if (!g_msm_copy_stream) {
+            ZK_CUDA(cudaStreamCreateWithFlags(&g_msm_copy_stream, cudaStreamNonBlocking));
+            for (auto& e : g_msm_part_ev) ZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const size_t per = align_up((n + parts - 1) / parts, 256);
+        ZK_CUDA(cudaEventRecord(g_msm_part_ev[MSM_MAX_PARTS], s));   // earlier users of the staging buffer
+        ZK_CUDA(cudaStreamWaitEvent(g_msm_copy_stream, g_msm_part_ev[MSM_MAX_PARTS], 0));
+        size_t nparts = 0;
+        for (size_t b = 0; b < n; b += per, ++nparts) {
+            const size_t len = std::min(per, n - b);
+            ZK_CUDA(cudaMemcpyAsync(ds + b, scalars + 4 * b, len * sizeof(Fr), cudaMemcpyHostToDevice, g_msm_copy_stream));
+            ZK_CUDA(cudaEventRecord(g_msm_part_ev[nparts], g_msm_copy_stream));
+        }
+        for (size_t p = 0; p < nparts; ++p) {
+            const size_t b = p * per, len = std::min(per, n - b);
+            ZK_CUDA(cudaStreamWaitEvent(s, g_msm_part_ev[p], 0));
+            MsmPart part;
+            part.first = p == 0; part.last = p + 1 == nparts; part.index_offset = (uint32_t)b;
+            msm_device(c, ds + b, len, 1, t->d, len, &pre, dout, s, part);
+        }
+        ZK_CUDA(cudaMemcpyAsync(out_xyz, dout, sizeof(G1Jacobian), cudaMemcpyDeviceToHost, s));
+        ZK_CUDA(cudaStreamSynchronize(s));
+        return;
+    }
+    if (n)
+        ZK_CUDA(cudaMemcpy2DAsync(ds, n * sizeof(Fr), scalars, stride * sizeof(Fr), n * sizeof(Fr), count,
+                                  cudaMemcpyHostToDevice, s));
+    msm_device(c, ds, n, count, t->d, n, t->table ? &pre : nullptr, dout, s);
+    ZK_CUDA(cudaMemcpyAsync(out_xyz, dout, count * sizeof(G1Jacobian), cudaMemcpyDeviceToHost, s));
+    ZK_CUDA(cudaStreamSynchronize(s));
+}
+
+int b200zk_msm_g1_registered(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]) {
+    return guarded([&] { msm_registered(handle, scalars, n, 1, n, out_xyz); });
+}
+
+int b200zk_msm_g1_registered_many(uint64_t handle, const uint64_t* scalars, size_t stride, size_t count, size_t n,
+                                  uint64_t* out_xyz) {
+    return guarded([&] { msm_registered(handle, scalars, stride, count, n, out_xyz); });
+}
+
+int b200zk_msm_g1_registered_dev(uint64_t handle, const void* d_scalars, size_t stride, size_t count, size_t n,
+                                 void* d_out_xyz, void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_out_xyz && (n == 0 || d_scalars), "null argument");
+        ZK_REQUIRE(count <= 1 || stride >= n, "batch stride smaller than the column");
+        ensure_init();
+        Context& c = ctx();
+        auto it = c.bases.find(handle);
+        ZK_REQUIRE(it != c.bases.end(), "unknown bases handle");
+        BaseTable* t = it->second;
+        ZK_REQUIRE(n <= t->n, "more scalars than registered bases");
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        MsmPre pre{t->table, t->n, t->c, t->nwin};
+        msm_device(c, (const Fr*)d_scalars, stride, count, t->d, n, t->table ? &pre : nullptr, (G1Jacobian*)d_out_xyz, s);
+    });
+}
+
+int b200zk_msm_g1_dev(const void* d_scalars, const void* d_bases, size_t n, uint64_t out_xyz[12], void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(out_xyz && (n == 0 || (d_scalars && d_bases)), "null argument");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        G1Jacobian* dout = (G1Jacobian*)c.misc.get(sizeof(G1Jacobian));
+        msm_device(c, (const Fr*)d_scalars, n, 1, (const G1Affine*)d_bases, n, nullptr, dout, s);
+        copy_point_out(c, dout, out_xyz, s);
+    });
+}
+
+int b200zk_msm_g1_dev_async(const void* d_scalars, const void* d_bases, size_t n, void* d_out_xyz, void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_out_xyz && (n == 0 || (d_scalars && d_bases)), "null argument");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        msm_device(c, (const Fr*)d_scalars, n, 1, (const G1Affine*)d_bases, n, nullptr, (G1Jacobian*)d_out_xyz, s);
+    });
+}
+
+int b200zk_msm_tune(uint32_t max_chunk, uint32_t max_seglen, uint32_t force_window_bits) {
+    return guarded([&] {
+        ZK_REQUIRE(max_chunk >= 4 && max_chunk <= 4096, "max_chunk out of range");
+        ZK_REQUIRE(max_seglen >= 4 && max_seglen <= 4096, "max_seglen out of range");
+        ZK_REQUIRE(force_window_bits == 0 || (force_window_bits >= 4 && force_window_bits <= 23), "window bits out of range");
+        g_msm_max_chunk = max_chunk;
+        g_msm_max_seglen = max_seglen;
+        g_msm_force_c = force_window_bits;
+    });
+}
+
+int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n) {
+    return guarded([&] {
+        ZK_REQUIRE(parts >= 1 && parts <= MSM_MAX_PARTS, "parts out of range");
+        g_msm_pipe_parts = parts;
+        g_msm_pipe_min_n = min_n;
+    });
+}
+
+int b200zk_msm_sort_mode(uint32_t mode, size_t partition_min_pairs) {
+    return guarded([&] {
+        ZK_REQUIRE(mode <= 2, "sort mode out of range");
+        g_msm_sort_mode = mode;
+        g_msm_partition_min_pairs = partition_min_pairs;
+    });
+}
+
+int b200zk_msm_profile(int enable) {
+    return guarded([&] { g_msm_profile = enable != 0; });
+}
+
+int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]) {
+    return guarded([&] {
+        ZK_REQUIRE(ms_out && capacity >= MSM_ST_COUNT - 1 && info_out, "bad arguments");
+        ZK_REQUIRE(g_msm_ev_made, "no profiled MSM has run");
+        ZK_CUDA(cudaStreamSynchronize(g_msm_ev_stream));
+        for (int i = 0; i + 1 < MSM_ST_COUNT; ++i) {
+            ms_out[i] = 0.f;
+            if (!g_msm_ev_valid[i]) continue;
+            int j = i + 1;
+            while (j < MSM_ST_COUNT && !g_msm_ev_valid[j]) ++j;
+            if (j < MSM_ST_COUNT) ZK_CUDA(cudaEventElapsedTime(&ms_out[i], g_msm_ev[i], g_msm_ev[j]));
+        }
+        info_out[0] = g_msm_info.n; info_out[1] = g_msm_info.c; info_out[2] = g_msm_info.nwin;
+        info_out[3] = g_msm_info.npairs; info_out[4] = g_msm_info.chunk;
+    });
+}
+
+int b200zk_g1_sum(const uint64_t* points_xyz, size_t count, uint64_t out_xyz[12]) {
+    return guarded([&] {
+        ZK_REQUIRE(out_xyz && (count == 0 || points_xyz), "null argument");
+        ZK_REQUIRE(count < (1u << 20), "too many points");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = c.stream;
+        G1Jacobian* d = (G1Jacobian*)c.misc.get((count + 1) * sizeof(G1Jacobian));
+        if (count) ZK_CUDA(cudaMemcpyAsync(d + 1, points_xyz, count * sizeof(G1Jacobian), cudaMemcpyHostToDevice, s));
+        g1_sum_kernel<<<1, 32, 0, s>>>(d + 1, (uint32_t)count, d);
+        ZK_LAUNCH_CHECK();
+        copy_point_out(c, d, out_xyz, s);
+    });
+}
+
+}  // extern "C"
