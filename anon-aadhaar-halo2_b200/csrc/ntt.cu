@@ -4,7 +4,9 @@
 #include "common.cuh"
 #include "ntt.cuh"
 
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 
 namespace zk {
 
@@ -78,6 +80,11 @@ void ntt_release_tables(Context& c) {
     c.ntt_tables.clear();
 }
 
+// transfer pipeline of the host-buffer entry points (one large transform): column ranges and the
+// size from which it is used
+static uint32_t g_ntt_pipe_chunks = getenv("B200ZK_NTT_PIPE_CHUNKS") ? (uint32_t)atoi(getenv("B200ZK_NTT_PIPE_CHUNKS")) : 4u;
+static uint32_t g_ntt_pipe_min_log_n = getenv("B200ZK_NTT_PIPE_MIN_LOG_N") ? (uint32_t)atoi(getenv("B200ZK_NTT_PIPE_MIN_LOG_N")) : 22u;
+
 struct NttMods {
     uint32_t in_mode = NTT_IN_PLAIN;
     uint32_t n_in = 0;  // 0 = all rows valid
@@ -117,8 +124,20 @@ template <bool FIRST> static void launch_pass_b(int b, const NttPassArgs& a, uns
 
 // Transform `count` columns of 2^log_n elements.  `in` may equal `out` (in place);
 // `tmp` must hold count * 2^log_n elements when more than one pass is needed.
+// `chunks` > 1 (single large transform from a host buffer): the first and the last pass are
+// launched in `chunks` column ranges; before_first(ch, col0, cols, rows) runs before range ch of
+// the first pass is launched, after_last(ch, col0, cols, rows) after range ch of the last pass.
+// A range of the first pass reads rows x [col0, col0 + cols) of the row-major [rows][ncols]
+// input, a range of the last pass writes the same shape of the output, so the caller can move
+// exactly those rectangles over PCIe while the other ranges compute.
+struct NttChunkHooks {
+    int chunks = 1;
+    std::function<void(int, uint64_t, uint64_t, uint64_t)> before_first, after_last;
+};
+
 static void ntt_run(Context& c, const Fr* in, uint64_t in_stride, Fr* out, uint64_t out_stride, Fr* tmp,
-                    size_t count, uint32_t log_n, const Fr& omega, const NttMods& mods, cudaStream_t s) {
+                    size_t count, uint32_t log_n, const Fr& omega, const NttMods& mods, cudaStream_t s,
+                    const NttChunkHooks* hooks = nullptr) {
     if (count == 0) return;
     NttTables* t = ntt_get_tables(c, omega, log_n, s);
     const uint64_t n = (uint64_t)1 << log_n;
@@ -162,7 +181,18 @@ static void ntt_run(Context& c, const Fr* in, uint64_t in_stride, Fr* out, uint6
         const uint32_t ncols = 1u << a.log_cols;
         const uint32_t C = 1u << (NTT_TILE_LOG - b);
         const unsigned blocks = (ncols + C - 1) / C;
-        if (p == 0) launch_pass_b<true>(b, a, blocks, (unsigned)count, s);
+        const bool chunked = hooks && hooks->chunks > 1 && P >= 2 && (p == 0 || p == P - 1) &&
+                             blocks % (unsigned)hooks->chunks == 0;
+        if (chunked) {
+            const unsigned per = blocks / (unsigned)hooks->chunks;
+            for (int ch = 0; ch < hooks->chunks; ++ch) {
+                a.block_offset = (uint32_t)ch * per;
+                if (p == 0 && hooks->before_first) hooks->before_first(ch, (uint64_t)a.block_offset * C, (uint64_t)per * C, (uint64_t)1 << b);
+                if (p == 0) launch_pass_b<true>(b, a, per, (unsigned)count, s);
+                else launch_pass_b<false>(b, a, per, (unsigned)count, s);
+                if (p == P - 1 && hooks->after_last) hooks->after_last(ch, (uint64_t)a.block_offset * C, (uint64_t)per * C, (uint64_t)1 << b);
+            }
+        } else if (p == 0) launch_pass_b<true>(b, a, blocks, (unsigned)count, s);
         else launch_pass_b<false>(b, a, blocks, (unsigned)count, s);
         src = dst;
         src_stride = dst_stride;
@@ -192,6 +222,60 @@ static void host_ntt(uint64_t* a, size_t stride, size_t count, uint32_t log_n, c
     cudaStream_t s = c.stream;
     Fr* io = (Fr*)c.ntt_io.get(count * n * sizeof(Fr));
     Fr* tmp = (Fr*)c.ntt_tmp.get(count * n * sizeof(Fr));
+    if (count == 1 && log_n >= g_ntt_pipe_min_log_n && g_ntt_pipe_chunks > 1) {
+        // one large transform: upload column ranges under the first pass, download under the last
+        constexpr int MAXC = 16;
+        static cudaStream_t up = nullptr, down = nullptr;
+        static cudaEvent_t ev_up[MAXC], ev_done[MAXC], ev_start;
+        if (!up) {
+            ZK_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+            ZK_CUDA(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+            for (int i = 0; i < MAXC; ++i) {
+                ZK_CUDA(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
+                ZK_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+            }
+            ZK_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        }
+        int chunks = std::min<int>((int)g_ntt_pipe_chunks, MAXC);
+        while (chunks & (chunks - 1)) chunks &= chunks - 1;          // power of two
+        NttTables* t = ntt_get_tables(c, omega, log_n, s);
+        bool uploaded = false;
+        if (t->npass >= 2) {
+            const uint64_t rows0 = (uint64_t)1 << t->bits[0], ncols0 = n >> t->bits[0];
+            // column tiles of the first and of the last pass: both must split into `chunks` ranges
+            const int bl = t->bits[t->npass - 1];
+            const uint64_t tiles_first = ncols0 >> std::min<uint64_t>(NTT_TILE_LOG - t->bits[0], 63);
+            const uint64_t tiles_last = (n >> bl) >> std::min<uint64_t>(NTT_TILE_LOG - bl, 63);
+            while (chunks > 1 && ((uint64_t)chunks > tiles_first || (uint64_t)chunks > tiles_last)) chunks >>= 1;
+            if (chunks > 1) {
+                ZK_CUDA(cudaEventRecord(ev_start, s));              // earlier users of the staging buffers
+                ZK_CUDA(cudaStreamWaitEvent(up, ev_start, 0));
+                const uint64_t cols = ncols0 / (uint64_t)chunks;
+                for (int ch = 0; ch < chunks; ++ch) {
+                    ZK_CUDA(cudaMemcpy2DAsync(io + ch * cols, ncols0 * sizeof(Fr), (const Fr*)a + ch * cols, ncols0 * sizeof(Fr),
+                                              cols * sizeof(Fr), rows0, cudaMemcpyHostToDevice, up));
+                    ZK_CUDA(cudaEventRecord(ev_up[ch], up));
+                }
+                uploaded = true;
+            }
+        }
+        if (uploaded) {
+            NttChunkHooks hooks;
+            hooks.chunks = chunks;
+            hooks.before_first = [&](int ch, uint64_t, uint64_t, uint64_t) { ZK_CUDA(cudaStreamWaitEvent(s, ev_up[ch], 0)); };
+            hooks.after_last = [&](int ch, uint64_t col0, uint64_t cols, uint64_t rows) {
+                const uint64_t ncols = n / rows;
+                ZK_CUDA(cudaEventRecord(ev_done[ch], s));
+                ZK_CUDA(cudaStreamWaitEvent(down, ev_done[ch], 0));
+                ZK_CUDA(cudaMemcpy2DAsync((Fr*)a + col0, ncols * sizeof(Fr), io + col0, ncols * sizeof(Fr), cols * sizeof(Fr), rows,
+                                          cudaMemcpyDeviceToHost, down));
+            };
+            ntt_run(c, io, n, io, n, tmp, 1, log_n, omega, mods, s, &hooks);
+            ZK_CUDA(cudaStreamSynchronize(s));
+            ZK_CUDA(cudaStreamSynchronize(down));
+            return;
+        }
+    }
     ZK_CUDA(cudaMemcpy2DAsync(io, n * sizeof(Fr), a, stride * sizeof(Fr), n * sizeof(Fr), count,
                               cudaMemcpyHostToDevice, s));
     ntt_run(c, io, n, io, n, tmp, count, log_n, omega, mods, s);
@@ -322,6 +406,14 @@ static __global__ void coset_interleave_kernel(const Fr* __restrict__ in, Fr* __
 using namespace zk;
 
 extern "C" {
+
+int b200zk_ntt_transfer_pipeline(uint32_t chunks, uint32_t min_log_n) {
+    return guarded([&] {
+        ZK_REQUIRE(chunks >= 1 && chunks <= 16 && (chunks & (chunks - 1)) == 0, "chunks must be a power of two <= 16");
+        g_ntt_pipe_chunks = chunks;
+        g_ntt_pipe_min_log_n = min_log_n;
+    });
+}
 
 int b200zk_ntt(uint64_t* a, uint32_t log_n, const uint64_t omega[4]) {
     return b200zk_ntt_many(a, (size_t)1 << log_n, 1, log_n, omega);

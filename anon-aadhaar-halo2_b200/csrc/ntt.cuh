@@ -54,6 +54,7 @@ struct NttPassArgs {
     uint32_t n_keep;     // outputs with i >= n_keep are not stored
     uint64_t in_batch_stride;   // elements between consecutive transforms of a batch
     uint64_t out_batch_stride;
+    uint32_t block_offset;      // first column tile of this launch (a pass may be launched in column ranges)
 };
 
 // Per-(omega, log_n) twiddle tables, built on the device once and cached (ntt.cu).
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(const __grid_c
     uint4* S0 = ntt_smem;
     uint4* S1 = ntt_smem + NTT_TILE;
     constexpr int LOGC = NTT_TILE_LOG - B;
-    const uint32_t m0 = blockIdx.x << LOGC;
+    const uint32_t m0 = (blockIdx.x + A.block_offset) << LOGC;
     const Fr* in = A.in + (uint64_t)blockIdx.y * A.in_batch_stride;
     Fr* out = A.out + (uint64_t)blockIdx.y * A.out_batch_stride;
     ntt_rounds_from<B, FIRST, 0>(A, in, out, S0, S1, threadIdx.x, m0);

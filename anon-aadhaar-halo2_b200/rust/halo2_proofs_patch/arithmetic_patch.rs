@@ -171,3 +171,33 @@ pub fn g1_to_bytes(points: &[G1]) -> Vec<[u8; 32]> {
     ffi::check(unsafe { ffi::b200zk_g1_to_bytes(points.as_ptr() as *const u64, points.len(), out.as_mut_ptr() as *mut u8) });
     out
 }
+
+// ---- page-locked host buffers ------------------------------------------------------------------
+/// RAII guard around `b200zk_host_register`: page-locks the backing store of a `Vec<Fr>` /
+/// `Polynomial` for as long as the guard lives, so the host-pointer entry points transfer at the
+/// full PCIe rate and the MSM upload / NTT transfer pipelines can overlap their copies (on a B200
+/// box: 72 ms instead of 170-179 ms for a 2^24 commit + transform from a pageable buffer).
+/// `create_proof` takes one guard per long-lived polynomial vector (advice, permutation products,
+/// lookup columns, h pieces); `ParamsKZG::read` takes one around the point buffer it registers.
+pub struct PageLocked<'a, T> {
+    slice: &'a [T],
+}
+
+impl<'a, T> PageLocked<'a, T> {
+    pub fn new(slice: &'a [T]) -> Self {
+        if !slice.is_empty() {
+            ffi::check(unsafe {
+                ffi::b200zk_host_register(slice.as_ptr() as *mut core::ffi::c_void, core::mem::size_of_val(slice))
+            });
+        }
+        PageLocked { slice }
+    }
+}
+
+impl<'a, T> Drop for PageLocked<'a, T> {
+    fn drop(&mut self) {
+        if !self.slice.is_empty() {
+            ffi::check(unsafe { ffi::b200zk_host_unregister(self.slice.as_ptr() as *mut core::ffi::c_void) });
+        }
+    }
+}

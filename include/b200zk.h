@@ -349,6 +349,11 @@ int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]);
  * the PCIe upload of range p+1 runs under the sort + accumulation of range p (same group
  * element).  parts = 1 disables it.  Defaults: 4 parts from 2^22 scalars. */
 int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n);
+/* Transfer pipeline of b200zk_ntt / b200zk_intt on one host buffer of at least 2^min_log_n
+ * elements: the first pass runs in `chunks` column ranges, each as soon as its rectangle of the
+ * input has arrived, and the last pass likewise, each rectangle of the output leaving while the
+ * next range computes (same result).  chunks = 1 disables it.  Defaults: 4 ranges from 2^22. */
+int b200zk_ntt_transfer_pipeline(uint32_t chunks, uint32_t min_log_n);
 /* Number of kernels launched by this library since init (for bench.py gpu_launches). */
 uint64_t b200zk_kernel_launches(void);
 

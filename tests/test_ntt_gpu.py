@@ -147,3 +147,28 @@ def test_full_size_properties(zk, k):
     zk.check(lib.b200zk_ntt_dev(C.c_void_p(buf.data_ptr()), n, 1, k, p(wil), p(ninv), None))
     torch.cuda.synchronize()
     assert torch.equal(buf, orig)
+
+
+@pytest.mark.parametrize("k,chunks", [(10, 2), (13, 4), (16, 8), (19, 4), (20, 16)])
+def test_host_transfer_pipeline_same_transform(zk, k, chunks):
+    """b200zk_ntt / b200zk_intt with the first and last pass launched in column ranges around
+    chunked 2-D transfers (the large-transform path, forced at small sizes): bit-identical to the
+    oracle, on pageable and on page-locked buffers."""
+    lib = zk.load()
+    n = 1 << k
+    a = co.gen_scalars(0xC0DE + k, n)
+    w = omega_for(k)
+    exp = co.best_fft(a, fr1(w), k)
+    d = zk.EvaluationDomain(3, k)
+    try:
+        zk.check(lib.b200zk_ntt_transfer_pipeline(chunks, 1))
+        got = a.copy()
+        zk.best_fft(got, w, k)
+        assert np.array_equal(got, exp)
+        with zk.pinned(a.copy()) as buf:
+            zk.best_fft(buf, w, k)
+            assert np.array_equal(buf, exp)
+        back = d.lagrange_to_coeff(exp.copy())            # intt: the divisor is fused into the chunked last pass
+        assert np.array_equal(back, a)
+    finally:
+        zk.check(lib.b200zk_ntt_transfer_pipeline(4, 22))
