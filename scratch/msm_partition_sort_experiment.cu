@@ -151,7 +151,7 @@ __global__ void msm_hist_kernel(const Fr* __restrict__ scalars, size_t scalar_st
         int32_t sd;
         if (d > half) { sd = (int32_t)d - (int32_t)(1u << c); carry = 1; }
         else { sd = (int32_t)d; carry = 0; }
-        if (valid && digits) digits[((size_t)col * nwin + w) * n + i] = sd;
+        if (valid) digits[((size_t)col * nwin + w) * n + i] = sd;
         // One atomic per distinct key in the warp: witness columns are full of repeated values
         // (all-equal scalars put every point of a window in one bucket), and same-address
         // atomics serialise.
@@ -281,21 +281,27 @@ __global__ void msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n,
 }
 
 // ------------------------------------------------------- 3'. two-level partition sort
-// The large-MSM replacement for hist + scan + scatter above.  The atomic scatter writes every
-// 4-byte entry at a random place of the sorted list (a DRAM sector read-modify-write each) and
-// bumps one L2 counter per pair.  Here the pairs are first partitioned into NB <= 1024 coarse
-// bins of 2^F consecutive bucket keys through a shared-memory staging tile, so global writes
-// are runs of consecutive 8-byte (key, value) pairs; then one CTA per coarse bin counts, scans
-// and scatters its bin with shared-memory counters, the 4-byte stores landing inside the bin's
-// own (L2-resident) slice of the sorted list.  Digits never go to memory.
-//   count      per tile: coarse histogram in shared memory -> coarse_hist (one padded counter per bin)
-//   scan       cstart[b] = exclusive prefix, cursor[b] = cstart[b], start[nkeys] = total
-//   partition  per tile: count, reserve [cursor[b], +cnt) per bin, stage pairs by bin, write runs
-//   bin sort   per bin: fine histogram -> start[key], then sorted[start[key]++] = value
+// The large-MSM replacement for hist + scan + scatter above, which bumps one L2 counter per
+// pair twice (atomic-throughput-bound) and writes every 4-byte entry at a random place of the
+// sorted list (a DRAM sector read-modify-write each).  Here digits never go to memory:
+//   count      per tile of points: coarse histogram (<= 2048 bins of 2^F consecutive bucket keys)
+//              in shared memory, flushed to one padded global counter per bin
+//   scan       cstart[b] = exclusive prefix; cursor[b] = cstart[b]; start[nkeys] = total
+//   partition  per tile: count again, reserve [cursor[b], +cnt) per bin, stage the (key, value)
+//              pairs by bin in shared memory, write them out as runs
+//   bin sort   a persistent grid of one CTA per SM walks the bins: fine histogram of the bin's
+//              2^F keys in shared memory -> start[key]; then sorted[start[key]++] = value.  Only
+//              gridDim.x slices of the sorted list (~100 K pairs each) are open at a time, so
+//              they stay in L2 until complete (one CTA per bin with all slices open at once
+//              thrashed through DRAM: 17.5 ms at k = 24).
+// Every per-pair atomic is a shared-memory one (~0.75 lanes/clk/SM measured).
 constexpr uint32_t PART_THREADS = 256;
-constexpr uint32_t PART_TILE_PAIRS = 12288;      // 96 KiB of staged pairs per CTA
-constexpr uint32_t PART_MAX_BINS = 1024;
+constexpr uint32_t PART_TILE_PAIRS = 10240;      // 80 KiB of staged pairs per CTA (2 CTAs per SM)
+constexpr uint32_t PART_MAX_BINS = 2048;
+constexpr uint32_t PART_COARSE_BITS = 11;
+constexpr uint32_t PART_MAX_FINE_BITS = 13;      // 2^13 shared-memory counters per bin CTA
 constexpr uint32_t PART_PAD = 32;                // one coarse counter per 128-byte line
+constexpr uint32_t BIN_THREADS = 1024;
 
 struct PartGeom {
     uint32_t c, nwin, key_windows, fine_bits, nbins, pts_per_thread;
@@ -317,11 +323,51 @@ __device__ __forceinline__ void part_point_pairs(const Fr* __restrict__ scalars,
     });
 }
 
-// cursor of coarse bin b = start of its first bucket (the fine prefix sums are known already)
-__global__ void msm_part_cursor_kernel(const uint32_t* __restrict__ start, uint32_t nbins, uint32_t fine_bits,
-                                       uint32_t* __restrict__ cursor) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nbins) cursor[(size_t)b * PART_PAD] = start[(size_t)b << fine_bits];
+__global__ void __launch_bounds__(PART_THREADS) msm_part_count_kernel(const Fr* __restrict__ scalars, PartGeom g,
+                                                                     uint32_t* __restrict__ coarse_hist) {
+    __shared__ uint32_t cnt[PART_MAX_BINS];
+    for (uint32_t b = threadIdx.x; b < g.nbins; b += PART_THREADS) cnt[b] = 0;
+    __syncthreads();
+    const uint32_t col = blockIdx.y;
+    const size_t tile_base = (size_t)blockIdx.x * PART_THREADS * g.pts_per_thread;
+    for (uint32_t j = 0; j < g.pts_per_thread; ++j) {
+        const size_t i = tile_base + (size_t)j * PART_THREADS + threadIdx.x;
+        if (i < g.n)
+            part_point_pairs(scalars, g, col, i, 0, 0, [&](uint32_t key, uint32_t) { atomicAdd(&cnt[key >> g.fine_bits], 1u); });
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < g.nbins; b += PART_THREADS)
+        if (cnt[b]) atomicAdd(coarse_hist + (size_t)b * PART_PAD, cnt[b]);
+}
+
+__global__ void __launch_bounds__(1024) msm_part_scan_kernel(const uint32_t* __restrict__ coarse_hist, uint32_t nbins,
+                                                            uint32_t* __restrict__ cstart, uint32_t* __restrict__ cursor,
+                                                            uint32_t* __restrict__ start_end, uint32_t* __restrict__ total) {
+    __shared__ uint32_t warp_sums[32];
+    constexpr uint32_t PER = PART_MAX_BINS / 1024;
+    uint32_t v[PER], t = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < PER; ++q) {
+        const uint32_t b = threadIdx.x * PER + q;
+        v[q] = b < nbins ? coarse_hist[(size_t)b * PART_PAD] : 0u;
+        t += v[q];
+    }
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(t, warp_sums, tot);
+#pragma unroll
+    for (uint32_t q = 0; q < PER; ++q) {
+        const uint32_t b = threadIdx.x * PER + q;
+        if (b < nbins) {
+            cstart[b] = ex;
+            cursor[(size_t)b * PART_PAD] = ex;
+        }
+        ex += v[q];
+    }
+    if (threadIdx.x == 0) {
+        cstart[nbins] = tot;
+        *start_end = tot;     // start[nkeys] = number of pairs
+        *total = tot;
+    }
 }
 
 __global__ void __launch_bounds__(PART_THREADS) msm_partition_kernel(const Fr* __restrict__ scalars, PartGeom g,
@@ -344,7 +390,7 @@ __global__ void __launch_bounds__(PART_THREADS) msm_partition_kernel(const Fr* _
             part_point_pairs(scalars, g, col, i, 0, 0, [&](uint32_t key, uint32_t) { atomicAdd(&cnt[key >> g.fine_bits], 1u); });
     }
     __syncthreads();
-    // exclusive scan of the PART_MAX_BINS counters: 4 consecutive bins per thread
+    // exclusive scan of the PART_MAX_BINS counters: PER consecutive bins per thread
     constexpr uint32_t PER = PART_MAX_BINS / PART_THREADS;
     uint32_t v[PER], t = 0;
 #pragma unroll
@@ -377,32 +423,75 @@ __global__ void __launch_bounds__(PART_THREADS) msm_partition_kernel(const Fr* _
     }
 }
 
-// The partitioned pair list is ordered by coarse bin, so CTAs scheduled together write into a
-// narrow band of the sorted list and bump a narrow band of bucket cursors: both stay in L2.
-constexpr uint32_t ORD_THREADS = 256;
-constexpr uint32_t ORD_PER_THREAD = 4;
-__global__ void __launch_bounds__(ORD_THREADS) msm_ordered_scatter_kernel(const unsigned long long* __restrict__ pairs,
-                                                                         uint32_t npairs_bound, const uint32_t* __restrict__ total,
-                                                                         uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
-    const uint32_t npairs = min(npairs_bound, *total);
-    const uint32_t base = blockIdx.x * (ORD_THREADS * ORD_PER_THREAD);
-    if (base >= npairs) return;
-    const uint32_t lane = threadIdx.x & 31u;
-    unsigned long long pr[ORD_PER_THREAD];
+// one batch of UNROLL pairs per thread, BIN_THREADS apart (coalesced, streaming)
+constexpr uint32_t BIN_UNROLL = 8;
+__device__ __forceinline__ void bin_load(const unsigned long long* __restrict__ pairs, uint32_t p0, uint32_t hi,
+                                         unsigned long long (&pr)[BIN_UNROLL]) {
 #pragma unroll
-    for (uint32_t u = 0; u < ORD_PER_THREAD; ++u) {
-        const uint32_t p = base + u * ORD_THREADS + threadIdx.x;
-        pr[u] = p < npairs ? __ldcs(pairs + p) : ~0ull;
+    for (uint32_t u = 0; u < BIN_UNROLL; ++u) {
+        const uint32_t p = p0 + u * BIN_THREADS + threadIdx.x;
+        pr[u] = p < hi ? __ldcs(pairs + p) : ~0ull;
     }
+}
+
+__global__ void __launch_bounds__(BIN_THREADS) msm_bin_sort_kernel(const unsigned long long* __restrict__ pairs,
+                                                                  const uint32_t* __restrict__ cstart, uint32_t fine_bits,
+                                                                  uint32_t nbins, uint32_t nkeys, uint32_t* __restrict__ start,
+                                                                  uint32_t* __restrict__ sorted) {
+    extern __shared__ uint32_t fine[];                                // 2^fine_bits counters
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t nfine = 1u << fine_bits;
+    constexpr uint32_t STEP = BIN_UNROLL * BIN_THREADS;
+    for (uint32_t bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
+        const uint32_t lo = cstart[bin], hi = cstart[bin + 1];
+        const uint32_t kbase = bin << fine_bits;
+        for (uint32_t q = threadIdx.x; q < nfine; q += BIN_THREADS) fine[q] = 0;
+        __syncthreads();
+        {   // fine histogram; the next batch is in flight while this one is counted
+            unsigned long long cur[BIN_UNROLL], nxt[BIN_UNROLL];
+            bin_load(pairs, lo, hi, cur);
+            for (uint32_t p0 = lo; p0 < hi; p0 += STEP) {
+                bin_load(pairs, p0 + STEP, hi, nxt);
 #pragma unroll
-    for (uint32_t u = 0; u < ORD_PER_THREAD; ++u) {
-        const uint32_t key = (uint32_t)(pr[u] >> 32);             // 0xffffffff for padding lanes
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
-        uint32_t pos = 0;
-        if (key != 0xffffffffu && lane == leader) pos = atomicAdd(cursor + key, (uint32_t)__popc(peers));
-        pos = __shfl_sync(0xffffffffu, pos, leader);
-        if (key != 0xffffffffu) sorted[pos + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)pr[u];
+                for (uint32_t u = 0; u < BIN_UNROLL; ++u)
+                    if (cur[u] != ~0ull) atomicAdd(&fine[(uint32_t)(cur[u] >> 32) - kbase], 1u);
+#pragma unroll
+                for (uint32_t u = 0; u < BIN_UNROLL; ++u) cur[u] = nxt[u];
+            }
+        }
+        __syncthreads();
+        // exclusive scan: consecutive `per` counters per thread
+        const uint32_t per = nfine > BIN_THREADS ? nfine / BIN_THREADS : 1u;
+        const uint32_t first = threadIdx.x * per;
+        uint32_t t = 0;
+        if (first < nfine)
+            for (uint32_t q = 0; q < per; ++q) t += fine[first + q];
+        uint32_t tot;
+        uint32_t ex = block_exclusive_scan(t, warp_sums, tot);
+        if (first < nfine)
+            for (uint32_t q = 0; q < per; ++q) {
+                const uint32_t cntq = fine[first + q];
+                fine[first + q] = ex;                                 // becomes the cursor
+                if (kbase + first + q < nkeys) start[kbase + first + q] = lo + ex;
+                ex += cntq;
+            }
+        __syncthreads();
+        {
+            unsigned long long cur[BIN_UNROLL], nxt[BIN_UNROLL];
+            bin_load(pairs, lo, hi, cur);
+            for (uint32_t p0 = lo; p0 < hi; p0 += STEP) {
+                bin_load(pairs, p0 + STEP, hi, nxt);
+#pragma unroll
+                for (uint32_t u = 0; u < BIN_UNROLL; ++u)
+                    if (cur[u] != ~0ull) {
+                        const uint32_t pos = lo + atomicAdd(&fine[(uint32_t)(cur[u] >> 32) - kbase], 1u);
+                        sorted[pos] = (uint32_t)cur[u];
+                    }
+#pragma unroll
+                for (uint32_t u = 0; u < BIN_UNROLL; ++u) cur[u] = nxt[u];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -688,6 +777,7 @@ static cudaEvent_t g_msm_part_ev[MSM_MAX_PARTS + 1];
 // sort of the (bucket, point) pairs: 0 = by size, 1 = atomic scatter, 2 = two-level partition
 static uint32_t g_msm_sort_mode = getenv("B200ZK_MSM_SORT_MODE") ? (uint32_t)atoi(getenv("B200ZK_MSM_SORT_MODE")) : 0u;
 static size_t g_msm_partition_min_pairs = getenv("B200ZK_MSM_PARTITION_MIN_PAIRS") ? (size_t)atoll(getenv("B200ZK_MSM_PARTITION_MIN_PAIRS")) : ((size_t)1 << 22);
+static uint32_t g_msm_bin_ctas_per_sm = getenv("B200ZK_MSM_BIN_CTAS_PER_SM") ? (uint32_t)atoi(getenv("B200ZK_MSM_BIN_CTAS_PER_SM")) : 1u;
 static uint32_t g_msm_force_sub = getenv("B200ZK_MSM_SUB_BITS") ? (uint32_t)atoi(getenv("B200ZK_MSM_SUB_BITS")) : 0xffffffffu;
 static cudaEvent_t g_msm_ev[MSM_ST_COUNT];
 static bool g_msm_ev_made = false, g_msm_ev_valid[MSM_ST_COUNT];
@@ -835,19 +925,19 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_buckets = carve((size_t)nkeys * sizeof(G1Xyzz));   // first: same place for every part of an MSM
     const size_t o_win = carve(groups * sizeof(G1Xyzz));
-    // sort method: two-level partition for large pair lists, atomic scatter otherwise
-    uint32_t key_bits = 0;
-    while (((size_t)1 << key_bits) < nkeys_sz) ++key_bits;
-    const uint32_t fine_bits = key_bits > 9 ? key_bits - 9 : 0;
-    const uint32_t nbins = (uint32_t)((nkeys_sz + ((size_t)1 << fine_bits) - 1) >> fine_bits);
-    const bool part_ok = nbins <= PART_MAX_BINS && PART_THREADS * nwin <= PART_TILE_PAIRS;
-    const bool use_partition = part_ok && (g_msm_sort_mode == 2 || (g_msm_sort_mode == 0 && max_pairs >= g_msm_partition_min_pairs));
     const size_t o_hist = carve(((size_t)nkeys + 1) * 4);
     const size_t o_start = carve(((size_t)nkeys + 1) * 4);
     const size_t o_cursor = carve(((size_t)nkeys + 1) * 4);
     const size_t o_bsum = carve(((size_t)scan_blocks + 1) * 4);
-    const size_t o_coarse = carve((size_t)PART_MAX_BINS * PART_PAD * 4);
     const size_t o_total = carve(256);
+    // sort method: two-level partition for large pair lists, atomic scatter otherwise
+    uint32_t key_bits = 0;
+    while (((size_t)1 << key_bits) < nkeys_sz) ++key_bits;
+    const uint32_t fine_bits = key_bits > PART_COARSE_BITS ? key_bits - PART_COARSE_BITS : 0;
+    const uint32_t nbins = (uint32_t)((nkeys_sz + ((size_t)1 << fine_bits) - 1) >> fine_bits);
+    const bool part_ok = fine_bits <= PART_MAX_FINE_BITS && nbins <= PART_MAX_BINS && PART_THREADS * nwin <= PART_TILE_PAIRS;
+    const bool use_partition = part_ok && (g_msm_sort_mode == 2 || (g_msm_sort_mode == 0 && max_pairs >= g_msm_partition_min_pairs));
+    const size_t o_coarse = carve(((size_t)2 * PART_MAX_BINS * PART_PAD + PART_MAX_BINS + 1) * 4);
     const size_t o_sorted = carve(max_pairs * 4);
     const size_t o_digits = carve(max_pairs * (use_partition ? 8 : 4));
     char* base = (char*)c.msm_work.get(off);
@@ -868,28 +958,21 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
         ZK_CUDA(cudaMemsetAsync(win, 0, groups * sizeof(G1Xyzz), s));
     }
     if (use_partition) {
-        // fine histogram (no digits stored) -> bucket offsets; partition by coarse bin; ordered scatter
         PartGeom g;
         g.c = cbits; g.nwin = nwin; g.key_windows = key_windows; g.fine_bits = fine_bits; g.nbins = nbins;
         g.pts_per_thread = std::max<uint32_t>(1, PART_TILE_PAIRS / (PART_THREADS * nwin));
         g.n = n; g.scalar_stride = scalar_stride;
         const unsigned tiles = (unsigned)((n + (size_t)PART_THREADS * g.pts_per_thread - 1) / ((size_t)PART_THREADS * g.pts_per_thread));
+        uint32_t* coarse_hist = (uint32_t*)(base + o_coarse);
+        uint32_t* coarse_cursor = coarse_hist + (size_t)PART_MAX_BINS * PART_PAD;
+        uint32_t* cstart = coarse_cursor + (size_t)PART_MAX_BINS * PART_PAD;      // nbins + 1
         unsigned long long* pairs = (unsigned long long*)digits;
-        uint32_t* coarse_cursor = (uint32_t*)(base + o_coarse);
-        ZK_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nkeys + 1) * 4, s));
-        const unsigned sblocks = (unsigned)((n + 255) / 256);
+        ZK_CUDA(cudaMemsetAsync(coarse_hist, 0, (size_t)nbins * PART_PAD * 4, s));
         T.mark(MSM_ST_HIST);
-        msm_hist_kernel<<<dim3(sblocks, (unsigned)count), 256, 0, s>>>(d_scalars, scalar_stride, n, cbits, nwin,
-                                                                        key_windows, hist, nullptr);
+        msm_part_count_kernel<<<dim3(tiles, (unsigned)count), PART_THREADS, 0, s>>>(d_scalars, g, coarse_hist);
         ZK_LAUNCH_CHECK();
         T.mark(MSM_ST_SCAN);
-        scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(hist, start, bsum, nkeys);
-        ZK_LAUNCH_CHECK();
-        scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(bsum, scan_blocks, total);
-        ZK_LAUNCH_CHECK();
-        scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, nkeys, total);
-        ZK_LAUNCH_CHECK();
-        msm_part_cursor_kernel<<<(nbins + 255) / 256, 256, 0, s>>>(start, nbins, fine_bits, coarse_cursor);
+        msm_part_scan_kernel<<<1, 1024, 0, s>>>(coarse_hist, nbins, cstart, coarse_cursor, start + nkeys, total);
         ZK_LAUNCH_CHECK();
         T.mark(MSM_ST_SCATTER);
         const size_t part_smem = 3 * PART_MAX_BINS * 4 + (size_t)PART_TILE_PAIRS * 8;
@@ -901,8 +984,8 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
         msm_partition_kernel<<<dim3(tiles, (unsigned)count), PART_THREADS, part_smem, s>>>(
             d_scalars, g, pre ? (uint32_t)pre->n_reg : 0u, part.index_offset, coarse_cursor, pairs);
         ZK_LAUNCH_CHECK();
-        const uint32_t ord_blocks = (uint32_t)((max_pairs + ORD_THREADS * ORD_PER_THREAD - 1) / (ORD_THREADS * ORD_PER_THREAD));
-        msm_ordered_scatter_kernel<<<ord_blocks, ORD_THREADS, 0, s>>>(pairs, (uint32_t)std::min<size_t>(max_pairs, 0xffffffffu), total, cursor, sorted);
+        const uint32_t bin_ctas = std::min<uint32_t>(nbins, (uint32_t)c.sm_count * g_msm_bin_ctas_per_sm);
+        msm_bin_sort_kernel<<<bin_ctas, BIN_THREADS, (size_t)4 << fine_bits, s>>>(pairs, cstart, fine_bits, nbins, nkeys, start, sorted);
         ZK_LAUNCH_CHECK();
     } else {
     ZK_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nkeys + 1) * 4, s));
