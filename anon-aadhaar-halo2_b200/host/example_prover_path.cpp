@@ -54,6 +54,7 @@ int main(int argc, char** argv) {
         dump("extended_omega", domain.extended_omega);
         std::printf("extended_k %u t_len %zu\n", domain.extended_k, domain.t_evaluations.size());
         halo2::ParamsKZG params(g_lagrange, g_lagrange);
+        halo2::PageLocked<halo2::Fr> pin_column(column);   // the witness column lives for the whole proof
         dump("commit_lagrange", params.commit_lagrange(column));
         auto coeff = domain.lagrange_to_coeff(column);
         dump_vec_digest("lagrange_to_coeff", coeff);

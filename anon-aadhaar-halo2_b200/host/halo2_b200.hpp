@@ -200,6 +200,21 @@ struct DevCol {
 }  // namespace detail
 
 // ff::BatchInvert: `a.iter_mut().batch_invert()`; zeros stay zero
+// RAII page-lock of a host vector (b200zk_host_register): the same guard the Rust shim takes around
+// the polynomial vectors of a proof, so host-pointer calls transfer at the full PCIe rate and the
+// MSM upload / NTT transfer pipelines can overlap their copies.
+template <class T> class PageLocked {
+public:
+    explicit PageLocked(std::vector<T>& v) : p_(v.empty() ? nullptr : v.data()) {
+        if (p_) check(b200zk_host_register(p_, v.size() * sizeof(T)));
+    }
+    ~PageLocked() { if (p_) b200zk_host_unregister(p_); }
+    PageLocked(const PageLocked&) = delete;
+    PageLocked& operator=(const PageLocked&) = delete;
+private:
+    void* p_;
+};
+
 inline void batch_invert(std::vector<Fr>& a) {
     if (!a.empty()) check(b200zk_batch_invert(a.data()->data(), a.size()));
 }
