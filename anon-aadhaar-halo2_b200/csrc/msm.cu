@@ -43,7 +43,10 @@ struct BaseTable {
     uint32_t c = 0, nwin = 0;
 };
 
+static void msm_release_pipeline();
+
 void msm_release_bases(Context& c) {
+    msm_release_pipeline();
     for (auto& kv : c.bases) {
         cudaFree(kv.second->d);
         if (kv.second->table) cudaFree(kv.second->table);
@@ -559,6 +562,12 @@ static size_t g_msm_pipe_parts = getenv("B200ZK_MSM_PIPE_PARTS") ? (size_t)atoi(
 static size_t g_msm_pipe_min_n = getenv("B200ZK_MSM_PIPE_MIN_N") ? (size_t)atoll(getenv("B200ZK_MSM_PIPE_MIN_N")) : ((size_t)1 << 22);
 static cudaStream_t g_msm_copy_stream = nullptr;
 static cudaEvent_t g_msm_part_ev[MSM_MAX_PARTS + 1];
+static void msm_release_pipeline() {          // b200zk_shutdown: the next init may bind another device
+    if (!g_msm_copy_stream) return;
+    cudaStreamDestroy(g_msm_copy_stream);
+    for (auto& e : g_msm_part_ev) cudaEventDestroy(e);
+    g_msm_copy_stream = nullptr;
+}
 static uint32_t g_msm_force_sub = getenv("B200ZK_MSM_SUB_BITS") ? (uint32_t)atoi(getenv("B200ZK_MSM_SUB_BITS")) : 0xffffffffu;
 static cudaEvent_t g_msm_ev[MSM_ST_COUNT];
 static bool g_msm_ev_made = false, g_msm_ev_valid[MSM_ST_COUNT];

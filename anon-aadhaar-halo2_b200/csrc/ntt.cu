@@ -72,7 +72,19 @@ NttTables* ntt_get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStrea
     return t;
 }
 
+// streams / events of the host-buffer transfer pipeline (host_ntt)
+constexpr int NTT_PIPE_MAX_CHUNKS = 16;
+static cudaStream_t g_ntt_up = nullptr, g_ntt_down = nullptr;
+static cudaEvent_t g_ntt_ev_up[NTT_PIPE_MAX_CHUNKS], g_ntt_ev_done[NTT_PIPE_MAX_CHUNKS], g_ntt_ev_start;
+
 void ntt_release_tables(Context& c) {
+    if (g_ntt_up) {                            // b200zk_shutdown: the next init may bind another device
+        cudaStreamDestroy(g_ntt_up);
+        cudaStreamDestroy(g_ntt_down);
+        for (int i = 0; i < NTT_PIPE_MAX_CHUNKS; ++i) { cudaEventDestroy(g_ntt_ev_up[i]); cudaEventDestroy(g_ntt_ev_done[i]); }
+        cudaEventDestroy(g_ntt_ev_start);
+        g_ntt_up = g_ntt_down = nullptr;
+    }
     for (NttTables* t : c.ntt_tables) {
         cudaFree(t->block);
         delete t;
@@ -224,9 +236,12 @@ static void host_ntt(uint64_t* a, size_t stride, size_t count, uint32_t log_n, c
     Fr* tmp = (Fr*)c.ntt_tmp.get(count * n * sizeof(Fr));
     if (count == 1 && log_n >= g_ntt_pipe_min_log_n && g_ntt_pipe_chunks > 1) {
         // one large transform: upload column ranges under the first pass, download under the last
-        constexpr int MAXC = 16;
-        static cudaStream_t up = nullptr, down = nullptr;
-        static cudaEvent_t ev_up[MAXC], ev_done[MAXC], ev_start;
+        constexpr int MAXC = NTT_PIPE_MAX_CHUNKS;
+        cudaStream_t& up = g_ntt_up;
+        cudaStream_t& down = g_ntt_down;
+        cudaEvent_t* ev_up = g_ntt_ev_up;
+        cudaEvent_t* ev_done = g_ntt_ev_done;
+        cudaEvent_t& ev_start = g_ntt_ev_start;
         if (!up) {
             ZK_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
             ZK_CUDA(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));

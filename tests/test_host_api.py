@@ -74,3 +74,39 @@ def test_page_locked_host_buffers(zk):
         zk.check(zk.load().b200zk_host_free(C.c_void_p(reg.ctypes.data)))
     zk.host_free(own)
     params.close()
+
+
+@pytest.mark.gpu
+def test_shutdown_and_reinit_with_pipelines(zk):
+    """b200zk_shutdown releases the pipeline streams / events together with everything else; the
+    library comes back with a fresh state and the same results."""
+    from oracle import c_oracle as co
+
+    lib = zk.load()
+    k = 12
+    n = 1 << k
+    s = co.gen_scalars(5, n)
+    g = co.gen_points(6, n)
+    w = zk.EvaluationDomain(3, k).omega
+    exp_fft = co.best_fft(s, w, k)
+    exp_pt = bn.g1_jacobian_limbs_to_affine(co.best_multiexp(s, g))
+
+    def run():
+        zk.check(lib.b200zk_msm_upload_pipeline(4, 1))
+        zk.check(lib.b200zk_ntt_transfer_pipeline(4, 1))
+        try:
+            params = zk.ParamsKZG(g, g)
+            got_pt = bn.g1_jacobian_limbs_to_affine(params.commit(s))
+            params.close()
+            a = s.copy()
+            zk.best_fft(a, w, k)
+            return got_pt, a
+        finally:
+            zk.check(lib.b200zk_msm_upload_pipeline(4, 1 << 22))
+            zk.check(lib.b200zk_ntt_transfer_pipeline(4, 22))
+
+    for _ in range(2):
+        got_pt, a = run()
+        assert got_pt == exp_pt and np.array_equal(a, exp_fft)
+        zk.shutdown()
+        zk.init(0)
