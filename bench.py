@@ -197,7 +197,7 @@ def run_reference(args) -> None:
     from oracle import c_oracle as co
     co.build()
     threads = co.host_threads()
-    k = args.cpu_k
+    k = args.cpu_k or 22
     n = 1 << k
     scalars = co.gen_scalars(SEED_S + k, n)
     points = co.gen_points(SEED_P + k, n, threads=threads)
@@ -239,7 +239,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--k", type=int, default=24, help="log2 points per GPU")
-    ap.add_argument("--cpu-k", type=int, default=20, help="log2 size of the bounded CPU sample")
+    ap.add_argument("--cpu-k", type=int, default=0,
+                    help="log2 size of the bounded CPU sample (0: min(k, 24) for cpu_baseline on the step's own inputs, "
+                         "22 for --impl reference)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -485,10 +487,17 @@ def main() -> None:
         from oracle import c_oracle as co
         co.build()
         threads = co.host_threads()
-        ck = args.cpu_k
-        secs, msm_s, fft_s = cpu_step(co, ck, threads)
+        ck = args.cpu_k or min(k, 24)
+        if ck == k:     # the step's own inputs (the seeded generators agree bit for bit, tests/test_oracle.py)
+            cpu_scalars = d_scal.cpu().numpy().view(np.uint64).reshape(n, 4).copy()
+            secs, msm_s, fft_s = cpu_step(co, ck, threads, cpu_scalars, h_bases_np)
+            del cpu_scalars
+            what = f"one whole step at 2^{ck} on the GPU arm's own inputs"
+        else:
+            secs, msm_s, fft_s = cpu_step(co, ck, threads)
+            what = f"one step at 2^{ck}"
         cpu_baseline = {"value": (1 << ck) / secs / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"one step at 2^{ck} (best_multiexp {msm_s:.2f} s + best_fft {fft_s:.2f} s); "
+                        "sample": f"{what} (best_multiexp {msm_s:.2f} s + best_fft {fft_s:.2f} s); "
                                   f"C restatement of the rayon CPU path, {threads} threads",
                         "msm_mpts_per_s": (1 << ck) / msm_s / 1e6, "ntt_melem_per_s": (1 << ck) / fft_s / 1e6}
 
