@@ -183,7 +183,7 @@ def cpu_step(co, k: int, threads: int, scalars=None, points=None):
         points = co.gen_points(SEED_P + k, n, threads=threads)
     w = fr_limbs(omega_for(k))
     t0 = time.perf_counter()
-    co.best_multiexp(scalars, points, threads)
+    cpu_step.last_point = co.best_multiexp(scalars, points, threads)
     t1 = time.perf_counter()
     co.best_fft(scalars, w, k, threads)
     t2 = time.perf_counter()
@@ -493,6 +493,10 @@ def main() -> None:
             secs, msm_s, fft_s = cpu_step(co, ck, threads, cpu_scalars, h_bases_np)
             del cpu_scalars
             what = f"one whole step at 2^{ck} on the GPU arm's own inputs"
+            # the CPU result doubles as a full-size parity check of the commit the GPU arm timed
+            from oracle import bn254 as bn
+            gpu_pt = d_pt.cpu().numpy().view(np.uint64)
+            msm_matches = bn.g1_jacobian_limbs_to_affine(gpu_pt) == bn.g1_jacobian_limbs_to_affine(cpu_step.last_point)
         else:
             secs, msm_s, fft_s = cpu_step(co, ck, threads)
             what = f"one step at 2^{ck}"
@@ -500,6 +504,8 @@ def main() -> None:
                         "sample": f"{what} (best_multiexp {msm_s:.2f} s + best_fft {fft_s:.2f} s); "
                                   f"C restatement of the rayon CPU path, {threads} threads",
                         "msm_mpts_per_s": (1 << ck) / msm_s / 1e6, "ntt_melem_per_s": (1 << ck) / fft_s / 1e6}
+        if ck == k:
+            cpu_baseline["same_commitment_as_gpu"] = bool(msm_matches)
 
     # ---- N > 1: ONE best_fft of 2^k sharded over all ranks (four-step, one exchange over NVLink)
     # (auxiliary legs never take the headline line down with them)
