@@ -24,6 +24,8 @@ static void plan_bits(uint32_t log_n, int& npass, int* bits) {
     for (int p = 0; p < npass; ++p) bits[p] = base + (p < rem ? 1 : 0);
 }
 
+static uint32_t g_ntt_direct_tw_max = getenv("B200ZK_NTT_DIRECT_TW_MAX_LOG_N") ? (uint32_t)atoi(getenv("B200ZK_NTT_DIRECT_TW_MAX_LOG_N")) : 20u;
+
 NttTables* ntt_get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStream_t s) {
     for (NttTables* t : c.ntt_tables)
         if (t->log_n == log_n && t->omega.same_limbs(omega)) return t;
@@ -32,7 +34,9 @@ NttTables* ntt_get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStrea
     t->omega = omega;
     t->log_n = log_n;
     plan_bits(log_n, t->npass, t->bits);
-    t->tw_h = (log_n + 1) / 2;
+    // inter-pass twiddle omega^e: one table of all n powers (one multiplication per element per pass
+    // boundary) up to 2^g_ntt_direct_tw_max elements, else lo/hi tables of sqrt(n) entries (two)
+    t->tw_h = log_n <= g_ntt_direct_tw_max ? log_n : (log_n + 1) / 2;
     const size_t n_lo = (size_t)1 << t->tw_h, n_hi = (size_t)1 << (log_n - t->tw_h);
     size_t total = n_lo + n_hi + 4;
     bool need[NTT_MAX_B + 1] = {};
