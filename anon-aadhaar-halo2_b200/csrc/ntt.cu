@@ -34,11 +34,22 @@ NttTables* ntt_get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStrea
     t->omega = omega;
     t->log_n = log_n;
     plan_bits(log_n, t->npass, t->bits);
-    // inter-pass twiddle omega^e: one table of all n powers (one multiplication per element per pass
-    // boundary) up to 2^g_ntt_direct_tw_max elements, else lo/hi tables of sqrt(n) entries (two)
-    t->tw_h = log_n <= g_ntt_direct_tw_max ? log_n : (log_n + 1) / 2;
+    // inter-pass twiddle omega^e, e = (i_p * J) << log_I: lo / hi tables of sqrt(n) entries (two
+    // multiplications), or, where the boundary's 2^(log_n - log_I) distinct exponents fit
+    // 2^g_ntt_direct_tw_max entries (L2-resident), one table of exactly those powers (one)
+    t->tw_h = (log_n + 1) / 2;
+    uint32_t direct_log[4] = {0, 0, 0, 0};
+    {
+        uint32_t log_I = 0;
+        for (int p = 0; p + 1 < t->npass; ++p) {
+            if (log_n - log_I <= g_ntt_direct_tw_max) direct_log[p] = log_n - log_I;
+            log_I += (uint32_t)t->bits[p];
+        }
+    }
     const size_t n_lo = (size_t)1 << t->tw_h, n_hi = (size_t)1 << (log_n - t->tw_h);
     size_t total = n_lo + n_hi + 4;
+    for (int p = 0; p < 4; ++p)
+        if (direct_log[p]) total += (size_t)1 << direct_log[p];
     bool need[NTT_MAX_B + 1] = {};
     for (int p = 0; p < t->npass; ++p) need[t->bits[p]] = true;
     for (int b = 1; b <= NTT_MAX_B; ++b)
@@ -58,6 +69,19 @@ NttTables* ntt_get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStrea
         if (!need[b]) continue;
         t->tw_tile[b] = cur; cur += (size_t)1 << b;
         fill(t->tw_tile[b], 1u << (log_n - b), 1u << b);
+    }
+    {
+        uint32_t log_I = 0;
+        for (int p = 0; p < 4; ++p) {
+            t->tw_direct[p] = nullptr;
+            if (p + 1 < t->npass) {
+                if (direct_log[p]) {
+                    t->tw_direct[p] = cur; cur += (size_t)1 << direct_log[p];
+                    fill(t->tw_direct[p], 1u << log_I, 1u << direct_log[p]);
+                }
+                log_I += (uint32_t)t->bits[p];
+            }
+        }
     }
     Fr* w8dev = cur;  // 4 entries: omega^(j * n/8), j = 0..3 (n >= 8), else unused
     if (log_n >= 3) {
@@ -184,6 +208,7 @@ static void ntt_run(Context& c, const Fr* in, uint64_t in_stride, Fr* out, uint6
         a.tw_lo = t->tw_lo;
         a.tw_hi = t->tw_hi;
         a.tw_h = t->tw_h;
+        a.tw_direct = (p + 1 < P) ? t->tw_direct[p] : nullptr;
         a.w8[0] = t->w8[0]; a.w8[1] = t->w8[1]; a.w8[2] = t->w8[2];
         a.in_mode = (p == 0) ? mods.in_mode : (uint32_t)NTT_IN_PLAIN;
         a.n_in = (p == 0 && mods.n_in) ? mods.n_in : (uint32_t)n;

@@ -55,6 +55,7 @@ struct NttPassArgs {
     uint64_t in_batch_stride;   // elements between consecutive transforms of a batch
     uint64_t out_batch_stride;
     uint32_t block_offset;      // first column tile of this launch (a pass may be launched in column ranges)
+    const Fr* tw_direct;        // omega^(x << log_I) for every x = i_p * J this pass can form, or null (lo / hi tables)
 };
 
 // Per-(omega, log_n) twiddle tables, built on the device once and cached (ntt.cu).
@@ -67,6 +68,7 @@ struct NttTables {
     Fr* tw_lo;                   // omega^x, x < 2^tw_h
     Fr* tw_hi;                   // omega^(y << tw_h)
     uint32_t tw_h;
+    Fr* tw_direct[4];            // per pass boundary p: (omega^(2^log_I_p))^x, x < n / 2^log_I_p, or null
     Fr w8[3];
     Fr* block;  // single allocation
 };
@@ -263,11 +265,17 @@ __device__ __forceinline__ void ntt_round(const NttPassArgs& A, const Fr* __rest
                 Fr x = v[g * SQ + a];
                 if (colok) {
                     if (!A.last) {
-                        const uint32_t e = (ip * Jv) << A.log_I;
-                        if (e != 0) {
-                            Fr t = ldg_fr(A.tw_lo + (e & ((1u << A.tw_h) - 1u)));
-                            const uint32_t eh = e >> A.tw_h;
-                            if (eh != 0) t = t * ldg_fr(A.tw_hi + eh);
+                        const uint32_t ex = ip * Jv;
+                        if (ex != 0) {
+                            Fr t;
+                            if (A.tw_direct) {
+                                t = ldg_fr(A.tw_direct + ex);
+                            } else {
+                                const uint32_t e = ex << A.log_I;
+                                t = ldg_fr(A.tw_lo + (e & ((1u << A.tw_h) - 1u)));
+                                const uint32_t eh = e >> A.tw_h;
+                                if (eh != 0) t = t * ldg_fr(A.tw_hi + eh);
+                            }
                             x = x * t;
                         }
                     }

@@ -222,6 +222,19 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def ntt_modmul_per_element(k: int) -> float:
+    """Multiplications per element of one 2^k transform as csrc/ntt.cu plans it: k/2 for the butterflies, and
+    per pass boundary one (a single table of the boundary's 2^(k - log_I) twiddles, used up to 2^20 entries) or
+    two (lo / hi tables)."""
+    npass = max(1, -(-k // 9))
+    bits = [k // npass + (1 if p < k % npass else 0) for p in range(npass)]
+    per, log_i = k / 2, 0
+    for p in range(npass - 1):
+        per += 1 if k - log_i <= 20 else 2
+        log_i += bits[p]
+    return per
+
+
 def workload_config(args, world: int) -> dict:
     return {
         "workload": f"BASELINE.json configs[1]: standalone BN254 MSM + Fr NTT at k={args.k} "
@@ -381,7 +394,7 @@ def main() -> None:
     except Exception:
         pass
     ntt_gbs = ntt_alg_bytes(k) / (ntt_ms * 1e-3) / 1e9
-    ntt_modmul = (1 << k) * (k / 2 + 2 * (max(1, -(-k // 9)) - 1)) / (ntt_ms * 1e-3)
+    ntt_modmul = (1 << k) * ntt_modmul_per_element(k) / (ntt_ms * 1e-3)
     roofline = {
         "kernel": "msm_accum_kernel", "bound": "int",
         "achieved": achieved_modmul / 1e9, "peak": peak_modmul / 1e9, "unit": "Gmodmul/s",
@@ -403,7 +416,7 @@ def main() -> None:
         "int_frac": ntt_modmul / peak_modmul,
         "traffic": traffic.get(f"ntt@k{k}"),
         "note": "254-bit butterflies make the transform integer-bound on B200: int_frac is the fraction of the "
-                "measured modmul peak (k/2 butterfly + 2 twiddle multiplications per element per pass boundary)",
+                "measured modmul peak (k/2 butterfly multiplications per element + 1 or 2 twiddle multiplications per pass boundary)",
     }
 
     # ---- the same MSM through plain best_multiexp (bases per call, no window table)
