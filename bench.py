@@ -691,8 +691,7 @@ def sweep(args, torch, b200zk, lib, dev) -> None:
         info = (C.c_uint64 * 5)()
         b200zk.check(lib.b200zk_msm_last_stages(ms, 9, info))
         acc = 10.0 * info[3] / (ms[4] * 1e-3)
-        passes = max(1, -(-k // 9))
-        ntt_mm = n * (k / 2 + 2 * (passes - 1)) / (ntt_ms * 1e-3)
+        ntt_mm = n * ntt_modmul_per_element(k) / (ntt_ms * 1e-3)
         rows.append({"k": k, "msm_ms": msm_ms, "msm_mpts_per_s": n / msm_ms / 1e3, "c": int(info[1]),
                      "accum_ms": ms[4], "accum_frac_of_modmul_peak": acc / peak,
                      "ntt_ms": ntt_ms, "ntt_alg_GBps": ntt_alg_bytes(k) / ntt_ms / 1e6,
