@@ -21,7 +21,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from ._lib import check, load
-from .api import EvaluationDomain, FR_ZETA, _ptr, fr_limbs
+from .api import EvaluationDomain, FR_ZETA, _ptr, fr_limbs, host_alloc_fr, host_free
 from .quotient import FR_DELTA, DeviceColumn, EnvC, FlatGraph, _handles, _ptr32
 
 
@@ -131,6 +131,11 @@ class ProverHotPath:
         self.h_coeff = DeviceColumn(n * (s.degree - 1))
         self.points = DeviceColumn((self.n_lag + 1 + s.degree - 1) * 3)   # 12 limbs = 3 field elements each
         self.seed = seed
+        # the advice columns come from witness synthesis on the CPU: a page-locked host copy that
+        # run() uploads inside its timed region (the other Lagrange columns are derived on the device)
+        self.host_advice = host_alloc_fr(s.advice * n)
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.lag.ptr), s.advice * n, seed + 2, 0))
+        check(lib.b200zk_dev_download(self.lag.handle, 0, _ptr(self.host_advice), s.advice * n))
         self.gates = gate_graph(s)
         self.lookup_graphs = [lookup_graph(s, j) for j in range(s.lookups)]
         rnd = np.random.Generator(np.random.PCG64(seed))
@@ -182,6 +187,9 @@ class ProverHotPath:
         check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.instance_coeff.ptr), self.instance_coeff.n, self.seed + 3, 0))
         self.sync()
         marks[0] = time.perf_counter()
+        # ---- the advice columns arrive from the host (witness synthesis)
+        check(lib.b200zk_dev_upload(self.lag.handle, 0, _ptr(self.host_advice), s.advice * n))
+        mark("upload_advice")
         # ---- commitments in Lagrange basis, one batch per prover phase
         col = 0
         for count in (s.advice, 2 * s.lookups, s.permutation_sets + s.lookups):
@@ -232,6 +240,8 @@ class ProverHotPath:
         mark("divide_and_extended_to_coeff")
         self._commit(self.h_coeff.ptr, s.degree - 1, self.n_lag + 1)
         mark("commit_h_pieces")
+        self.commitments = self.points.to_host()           # every commitment of the proof back on the host
+        mark("download_commitments")
         t_ev.free()
         t["total"] = sum(t.values())
         return t
@@ -394,6 +404,9 @@ class ProverHotPath:
 
     def close(self) -> None:
         self.lib.b200zk_bases_evict(self.h_bases)
+        if getattr(self, "host_advice", None) is not None:
+            host_free(self.host_advice)
+            self.host_advice = None
         for v in self.ext_views + self.fixed + self.sigma + [self.l0, self.l_last, self.l_active]:
             v.free()
         for q, (col, views) in getattr(self, "pk_coset", {}).items():

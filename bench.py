@@ -618,7 +618,7 @@ def run_proof_shape(torch, dist, world: int, rank: int, dev, cpu: bool):
                    "exchange": "all-gather of coefficient columns (NCCL) + all-gather of evaluated h cosets"}
     out = {"workload": "synthetic stand-in for BASELINE.json configs[2] (RSA-SHA256 sub-circuit proof): the commit / "
                        "iNTT / coset-NTT / evaluate_h / extended_to_coeff calls of one create_proof on seeded random "
-                       "columns of the circuit's shape; witness synthesis, transcript and SHPLONK opening excluded",
+                       "columns of the circuit's shape; the advice columns are uploaded from page-locked host memory and every commitment is downloaded inside the timed region; witness synthesis, transcript and SHPLONK opening excluded",
            "calls": hp.counts(), "stages_ms": med, "hot_path_ms": float(tt.item()),
            "proofs_per_s_all_gpus": world / (float(tt.item()) * 1e-3), "parallelism": "replicas only",
            "sharded": sharded}
