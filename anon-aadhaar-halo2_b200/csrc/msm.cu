@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(128) msm_combine_warp_kernel(const uint32_t* _
 // Thread (w, seg) walks `seglen` buckets of window w from the top: run += B_b,
 // sum += run, then emits  sum + (lo-1) * run  with key w, where lo is the weight of the
 // segment's lowest bucket.  The sum over a window's segments is sum_b b * B_b.
-__global__ void __launch_bounds__(128, 4) msm_reduce_kernel(const G1Xyzz* __restrict__ buckets, uint32_t nb, uint32_t seglen,
+__global__ void __launch_bounds__(128, 3) msm_reduce_kernel(const G1Xyzz* __restrict__ buckets, uint32_t nb, uint32_t seglen,
                                                          uint32_t segs_per_win, uint32_t nwin,
                                                          uint32_t* __restrict__ out_key, G1Xyzz* __restrict__ out_pt) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -17,6 +17,7 @@ hb = db.cpu().numpy().view(np.uint64).reshape(n, 8)
 h = C.c_uint64(0)
 b200zk.check(lib.b200zk_bases_register(C.c_void_p(hb.ctypes.data), n, C.byref(h)))
 d_out = torch.zeros(12, dtype=torch.int64, device="cuda")
+if os.environ.get('SEGLEN'): b200zk.check(lib.b200zk_msm_tune(128, int(os.environ['SEGLEN']), 0))
 b200zk.check(lib.b200zk_msm_profile(1))
 with torch.cuda.stream(stream):
     run = lambda: b200zk.check(lib.b200zk_msm_g1_registered_dev(h.value, C.c_void_p(ds.data_ptr()), n, 1, n, C.c_void_p(d_out.data_ptr()), st))
@@ -26,5 +27,5 @@ with torch.cuda.stream(stream):
 ms = (C.c_float * 9)(); info = (C.c_uint64 * 5)()
 b200zk.check(lib.b200zk_msm_last_stages(ms, 9, info))
 aff = bn.g1_jacobian_limbs_to_affine(d_out.cpu().numpy().view(np.uint64))
-print(f"mode={os.environ.get('B200ZK_MSM_SORT_MODE','0')} l2mb={os.environ.get('B200ZK_MSM_BIN_L2_MB','-')} k={k} total={e0.elapsed_time(e1)/3:.3f}ms "
+print(f"seglen={os.environ.get('SEGLEN','-')} mode={os.environ.get('B200ZK_MSM_SORT_MODE','0')} l2mb={os.environ.get('B200ZK_MSM_BIN_L2_MB','-')} k={k} total={e0.elapsed_time(e1)/3:.3f}ms "
       f"x={aff[0] % 1000003} | " + " ".join(f"{nm}={v:.3f}" for nm, v in zip(names, ms)), flush=True)
