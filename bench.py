@@ -242,6 +242,9 @@ def workload_config(args, world: int) -> dict:
         "k": args.k, "points_per_gpu": 1 << args.k, "global_points": world << args.k,
         "parallelism": f"point-range split x{world}, one-point-per-rank gather" if world > 1 else "single GPU",
         "l2": "inputs (96 B/point + 32 B/NTT element, >= 2 GiB at k=24) exceed the 126 MB L2; no flush needed",
+        "streams": ("transform on a second, lower-priority stream under the commit (its kernel time below is the "
+                    "stretched, concurrent one)") if getattr(args, "overlap", False)
+                   else "commit and transform back to back on one stream",
     }
 
 
@@ -258,6 +261,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="issue the transform on a second, lower-priority stream under the commit")
     ap.add_argument("--sweep", action="store_true", help="print the k=16..26 table instead of the driver line")
     ap.add_argument("--no-proof-shape", action="store_true",
                     help="skip the RSA-SHA256-shaped create_proof hot-path pass (BASELINE.json configs[2] stand-in)")
@@ -292,7 +297,7 @@ def main() -> None:
         return
 
     k, n = args.k, 1 << args.k
-    stream = torch.cuda.Stream(device=dev)
+    stream = torch.cuda.Stream(device=dev, priority=-1)
     st = C.c_void_p(stream.cuda_stream)
     vp = lambda t: C.c_void_p(t.data_ptr())
 
@@ -322,20 +327,37 @@ def main() -> None:
         torch.cuda.synchronize()
 
     ntt_ev = []
+    # The commit and the transform of a step are independent (as the column commitments and transforms of
+    # create_proof are).  With --overlap the transform is issued on a second, lower-priority stream right
+    # after the commit's kernels are queued: its CTAs fill the SM slots the commit leaves idle (the
+    # latency-bound bucket reduction runs at ~12 % warp occupancy), and the step ends when both are done.
+    lo_stream = torch.cuda.Stream(device=dev, priority=0)
+    st_lo = C.c_void_p(lo_stream.cuda_stream)
 
     def step(timed: bool):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
+            if args.overlap:
+                fork = torch.cuda.Event()
+                fork.record(stream)
             b200zk.check(lib.b200zk_msm_g1_registered_dev(handle.value, vp(d_scal), n, 1, n, vp(d_pt), st))
+            if args.overlap:
+                lo_stream.wait_event(fork)                 # not before this step began
+                e0.record(lo_stream)
+                b200zk.check(lib.b200zk_ntt_dev(vp(d_ntt), n, 1, k, _ptr(omega), None, st_lo))
+                e1.record(lo_stream)
             if world > 1:
                 dist.all_gather_into_tensor(gathered, d_pt)
                 if rank == 0:
                     pts = gathered.cpu().numpy().view(np.uint64).reshape(world, 12)
                     result_holder["point"] = b200zk.g1_sum(np.ascontiguousarray(pts))
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            b200zk.check(lib.b200zk_ntt_dev(vp(d_ntt), n, 1, k, _ptr(omega), None, st))
-            e1.record(stream)
+            if args.overlap:
+                stream.wait_event(e1)                      # join
+            else:
+                e0.record(stream)
+                b200zk.check(lib.b200zk_ntt_dev(vp(d_ntt), n, 1, k, _ptr(omega), None, st))
+                e1.record(stream)
             if timed:
                 ntt_ev.append((e0, e1))
 
