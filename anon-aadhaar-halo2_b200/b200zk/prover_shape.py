@@ -246,6 +246,73 @@ class ProverHotPath:
         t["total"] = sum(t.values())
         return t
 
+    # ------------------------------------------------------------ the same proof with the phases overlapped
+    def run_overlapped(self, torch, hi_stream, lo_stream) -> dict:
+        """The stages of run() as a prover that owns both sides would issue them: the commitments on a
+        high-priority stream, the transforms of the same columns (lagrange_to_coeff on a copy, then
+        coeff_to_extended) on a lower-priority stream, whose CTAs fill the SM slots the commitments'
+        latency-bound bucket reductions leave idle; the quotient waits for both.  Same results as
+        run() (tests/test_prover_shape_gpu.py); returns the wall-clock total only, since the stages no
+        longer have separate times."""
+        lib, s, d, n, N = self.lib, self.shape, self.domain, self.n, self.N
+        hi, lo = C.c_void_p(hi_stream.cuda_stream), C.c_void_p(lo_stream.cuda_stream)
+        if not hasattr(self, "coef"):
+            self.coef = DeviceColumn(self.n_lag * n)
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.lag.ptr), self.lag.n, self.seed + 2, 0))
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.instance_coeff.ptr), self.instance_coeff.n, self.seed + 3, 0))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        check(lib.b200zk_dev_upload(self.lag.handle, 0, _ptr(self.host_advice), s.advice * n))
+        lag_t = self._torch_view(torch, self.lag, 0, self.n_lag * n)
+        coef_t = self._torch_view(torch, self.coef, 0, self.n_lag * n)
+        with torch.cuda.stream(lo_stream):
+            coef_t.copy_(lag_t, non_blocking=True)
+        check(lib.b200zk_ntt_dev(C.c_void_p(self.coef.ptr), n, self.n_lag, d.k, _ptr(d.omega_inv), _ptr(d.ifft_divisor), lo))
+        check(lib.b200zk_coeff_to_extended_dev(C.c_void_p(self.coef.ptr), n, C.c_void_p(self.ext.ptr), N, self.n_lag,
+                                               d.k, d.extended_k, _ptr(d.extended_omega), _ptr(d.g_coset), lo))
+        check(lib.b200zk_coeff_to_extended_dev(C.c_void_p(self.instance_coeff.ptr), n,
+                                               C.c_void_p(self.ext.ptr + self.n_lag * N * 32), N, s.instance, d.k,
+                                               d.extended_k, _ptr(d.extended_omega), _ptr(d.g_coset), lo))
+        col = 0
+        for count in (s.advice, 2 * s.lookups, s.permutation_sets + s.lookups):
+            out = self.points.ptr + col * 96
+            check(lib.b200zk_msm_g1_registered_dev(self.h_bases, C.c_void_p(self.lag.ptr + col * n * 32), n, count, n,
+                                                   C.c_void_p(out), hi))
+            col += count
+        torch.cuda.synchronize()
+        # ---- evaluate_h and the quotient's way back, as in run()
+        env = self._env()
+        g = self.gates.as_c()
+        check(lib.b200zk_quotient_graph(C.byref(g), C.byref(env), 0, self.values.handle))
+        lk0 = s.advice
+        pp0 = s.advice + 2 * s.lookups
+        lp0 = pp0 + s.permutation_sets
+        products = self.ext_views[pp0: pp0 + s.permutation_sets]
+        sig, ph = _handles(self.sigma), _handles(products)
+        zeta, delta = fr_limbs(FR_ZETA), fr_limbs(FR_DELTA)
+        check(lib.b200zk_quotient_permutation(
+            C.byref(env), self.values.handle, _ptr32(self.perm_kind), _ptr32(self.perm_index), _ptr(sig),
+            len(self.perm_kind), _ptr(ph), len(products), s.degree - 2, s.blinding_factors, self.l0.handle,
+            self.l_last.handle, self.l_active.handle, _ptr(d.extended_omega), _ptr(zeta), _ptr(delta)))
+        for j in range(s.lookups):
+            lg = self.lookup_graphs[j].as_c()
+            check(lib.b200zk_quotient_graph(C.byref(lg), C.byref(env), 0, self.table.handle))
+            check(lib.b200zk_quotient_lookup(C.byref(env), self.values.handle, self.table.handle,
+                                             self.ext_views[lp0 + j].handle, self.ext_views[lk0 + 2 * j].handle,
+                                             self.ext_views[lk0 + 2 * j + 1].handle, self.l0.handle,
+                                             self.l_last.handle, self.l_active.handle))
+        t_ev = DeviceColumn.from_host(d.t_evaluations)
+        keep = n * (s.degree - 1)
+        check(lib.b200zk_extended_to_coeff_dev(C.c_void_p(self.values.ptr), d.extended_k, _ptr(d.extended_omega_inv),
+                                               _ptr(d.extended_ifft_divisor), _ptr(d.g_coset), C.c_void_p(t_ev.ptr),
+                                               d.t_evaluations.shape[0], C.c_void_p(self.h_coeff.ptr), keep, None))
+        self._commit(self.h_coeff.ptr, s.degree - 1, self.n_lag + 1)
+        self.commitments = self.points.to_host()
+        torch.cuda.synchronize()
+        total = 1e3 * (time.perf_counter() - t0)
+        t_ev.free()
+        return {"total": total}
+
     # ------------------------------------------------------------ one proof over several GPUs
     # SURVEY.md section 8 e: commitments and iNTTs are dealt by column, the coefficient columns are
     # all-gathered (the one bulk exchange), every rank extends and evaluates only "its" cosets of the
@@ -415,7 +482,7 @@ class ProverHotPath:
             col.free()
         for v in getattr(self, "cos_views", []):
             v.free()
-        for name in ("lag_pad", "coef_all", "cos", "h_mine", "h_all"):
+        for name in ("lag_pad", "coef_all", "cos", "h_mine", "h_all", "coef"):
             if hasattr(self, name):
                 getattr(self, name).free()
         for c in (self.pk_cols, self.lag, self.instance_coeff, self.ext, self.values, self.table, self.h_coeff,
