@@ -529,6 +529,55 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const G1Affine* __r
     }
 }
 
+// The same table with one field inversion per point instead of one per table entry (380 of the
+// 580 multiplications an entry costs above): the doubling chain runs unnormalised, every multiple is
+// parked as (x, y) in its table slot and (zz, zzz, running product of the zzz) in `tmp`; the single
+// inverse of the total product is then peeled back window by window (Montgomery's trick along the
+// chain) and the slots are rewritten in affine form.  tmp holds 3 field elements per entry of
+// windows 1 .. nwin-1.  Bit-identical table.
+__global__ void __launch_bounds__(128) msm_precompute_batched_kernel(const G1Affine* __restrict__ bases, size_t n, uint32_t c,
+                                                                     uint32_t nwin, G1Affine* __restrict__ table,
+                                                                     Fq* __restrict__ tmp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p;
+    p.x = ldg_fq(&bases[i].x);
+    p.y = ldg_fq(&bases[i].y);
+    st_fq(&table[i].x, p.x);
+    st_fq(&table[i].y, p.y);
+    if (p.is_identity()) {
+        for (uint32_t w = 1; w < nwin; ++w) {
+            st_fq(&table[(size_t)w * n + i].x, p.x);
+            st_fq(&table[(size_t)w * n + i].y, p.y);
+        }
+        return;
+    }
+    G1Xyzz a = G1Xyzz::double_affine(p);
+    Fq prod = Fq::one();
+    for (uint32_t w = 1; w < nwin; ++w) {
+        for (uint32_t k = (w == 1 ? 1u : 0u); k < c; ++k) a = a.dbl();
+        Fq* t = tmp + ((size_t)(w - 1) * n + i) * 3;
+        st_fq(&table[(size_t)w * n + i].x, a.x);
+        st_fq(&table[(size_t)w * n + i].y, a.y);
+        st_fq(t, a.zz);
+        st_fq(t + 1, a.zzz);
+        st_fq(t + 2, prod);                       // product of the zzz of windows 1 .. w-1
+        prod = prod * a.zzz;
+    }
+    Fq inv = prod.inverse();                      // 1 / (zzz_1 ... zzz_{nwin-1})
+    for (uint32_t w = nwin - 1; w >= 1; --w) {
+        const Fq* t = tmp + ((size_t)(w - 1) * n + i) * 3;
+        const Fq zz = ld_fq(t), zzz = ld_fq(t + 1), before = ld_fq(t + 2);
+        const Fq zi = inv * before;               // 1 / zzz_w
+        inv = inv * zzz;
+        const Fq zzi = zi.sqr() * zz.sqr();       // 1 / zz_w = z^-6 z^4
+        G1Affine* slot = &table[(size_t)w * n + i];
+        const Fq x = ld_fq(&slot->x), y = ld_fq(&slot->y);
+        st_fq(&slot->x, (x * zzi).canon());
+        st_fq(&slot->y, (y * zi).canon());
+    }
+}
+
 __global__ void g1_sum_kernel(const G1Jacobian* __restrict__ pts, uint32_t count, G1Jacobian* out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     G1Xyzz acc = G1Xyzz::identity();
@@ -880,9 +929,21 @@ static void register_bases(const uint64_t* bases, size_t n, int precompute, uint
         ZK_CUDA(cudaMemGetInfo(&free_b, &total_b));
         if (n * (size_t)t->nwin < ((size_t)1 << 31) && bytes < free_b / 2) {
             ZK_CUDA(cudaMalloc(&t->table, bytes));
-            msm_precompute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(t->d, n, t->c, t->nwin, t->table);
+            // one inversion per point needs 96 B of scratch per table entry; fall back to one inversion
+            // per entry when that does not fit next to the table
+            Fq* tmp = nullptr;
+            const size_t tmp_bytes = n * (size_t)(t->nwin - 1) * 3 * sizeof(Fq);
+            if (t->nwin > 1 && cudaMalloc(&tmp, tmp_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                tmp = nullptr;
+            }
+            if (tmp)
+                msm_precompute_batched_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(t->d, n, t->c, t->nwin, t->table, tmp);
+            else
+                msm_precompute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(t->d, n, t->c, t->nwin, t->table);
             ZK_LAUNCH_CHECK();
             ZK_CUDA(cudaStreamSynchronize(c.stream));
+            if (tmp) cudaFree(tmp);
         }  // otherwise: plain registered bases (generic pipeline)
     }
     const uint64_t h = c.next_handle++;
