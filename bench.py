@@ -490,6 +490,25 @@ def main() -> None:
                "ms_per_step": 1e3 * dt / args.steps,
                "api": "b200zk_msm_g1_registered (ParamsKZG::commit_lagrange: scalars from pinned host memory, "
                       "SRS resident) + b200zk_ntt (best_fft in place on a pinned host buffer)"}
+        # the host-buffer calls (upload pipeline, transfer pipeline) against the device-resident ones on the
+        # same inputs: the commitment in canonical compressed form, the transform element for element
+        if rank == 0 and world == 1:
+            try:
+                dev_pt = d_pt.cpu().numpy().view(np.uint64).reshape(1, 12)
+                same_pt = bool(np.array_equal(b200zk.g1_to_bytes(np.ascontiguousarray(out.reshape(1, 12))),
+                                              b200zk.g1_to_bytes(np.ascontiguousarray(dev_pt))))
+                chk = torch.empty(n * 4, dtype=torch.int64, pin_memory=True)
+                chk.copy_(d_scal)
+                d_chk = d_scal.clone()
+                torch.cuda.synchronize()
+                b200zk.check(lib.b200zk_ntt(vp(chk), k, _ptr(omega)))
+                b200zk.check(lib.b200zk_ntt_dev(vp(d_chk), n, 1, k, _ptr(omega), None, None))
+                torch.cuda.synchronize()
+                same_ntt = bool(torch.equal(chk, d_chk.cpu()))
+                e2e["same_results_as_device_resident_calls"] = same_pt and same_ntt
+                del chk, d_chk
+            except Exception as ex:   # auxiliary: never take the headline line down
+                e2e["verify_error"] = str(ex)[:200]
         # informational: the same two calls on a pageable numpy buffer (what a Rust Vec<Fr> is), and on
         # that buffer after b200zk_host_register (what the shim does once per long-lived buffer)
         if rank == 0 and world == 1:
