@@ -109,6 +109,7 @@ def load() -> C.CDLL:
         "b200zk_msm_tune": ([u32, u32, u32], C.c_int),
         "b200zk_msm_upload_pipeline": ([u32, sz], C.c_int),
         "b200zk_ntt_transfer_pipeline": ([u32, u32], C.c_int),
+        "b200zk_ntt_tune": ([u32], C.c_int),
         "b200zk_msm_last_stages": ([C.POINTER(C.c_float), C.c_int, u64p], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():

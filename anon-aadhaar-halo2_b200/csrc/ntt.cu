@@ -105,6 +105,14 @@ constexpr int NTT_PIPE_MAX_CHUNKS = 16;
 static cudaStream_t g_ntt_up = nullptr, g_ntt_down = nullptr;
 static cudaEvent_t g_ntt_ev_up[NTT_PIPE_MAX_CHUNKS], g_ntt_ev_done[NTT_PIPE_MAX_CHUNKS], g_ntt_ev_start;
 
+static void ntt_drop_tables(Context& c) {
+    for (NttTables* t : c.ntt_tables) {
+        cudaFree(t->block);
+        delete t;
+    }
+    c.ntt_tables.clear();
+}
+
 void ntt_release_tables(Context& c) {
     if (g_ntt_up) {                            // b200zk_shutdown: the next init may bind another device
         cudaStreamDestroy(g_ntt_up);
@@ -113,11 +121,7 @@ void ntt_release_tables(Context& c) {
         cudaEventDestroy(g_ntt_ev_start);
         g_ntt_up = g_ntt_down = nullptr;
     }
-    for (NttTables* t : c.ntt_tables) {
-        cudaFree(t->block);
-        delete t;
-    }
-    c.ntt_tables.clear();
+    ntt_drop_tables(c);
 }
 
 // transfer pipeline of the host-buffer entry points (one large transform): column ranges and the
@@ -456,6 +460,19 @@ int b200zk_ntt_transfer_pipeline(uint32_t chunks, uint32_t min_log_n) {
         ZK_REQUIRE(chunks >= 1 && chunks <= 16 && (chunks & (chunks - 1)) == 0, "chunks must be a power of two <= 16");
         g_ntt_pipe_chunks = chunks;
         g_ntt_pipe_min_log_n = min_log_n;
+    });
+}
+
+int b200zk_ntt_tune(uint32_t direct_twiddle_max_log_n) {
+    return guarded([&] {
+        ZK_REQUIRE(direct_twiddle_max_log_n <= 28, "direct_twiddle_max_log_n out of range (0..28)");
+        Context& c = ctx();
+        if (c.ready) {                 // cached tables were planned under the old setting
+            ZK_CUDA(cudaSetDevice(c.device));
+            ZK_CUDA(cudaDeviceSynchronize());
+            ntt_drop_tables(c);
+        }
+        g_ntt_direct_tw_max = direct_twiddle_max_log_n;
     });
 }
 

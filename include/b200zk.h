@@ -354,6 +354,12 @@ int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n);
  * input has arrived, and the last pass likewise, each rectangle of the output leaving while the
  * next range computes (same result).  chunks = 1 disables it.  Defaults: 4 ranges from 2^22. */
 int b200zk_ntt_transfer_pipeline(uint32_t chunks, uint32_t min_log_n);
+/* Inter-pass twiddles of the NTT: a pass boundary whose 2^(log_n - log_I) distinct twiddles fit
+ * 2^direct_twiddle_max_log_n entries reads one table of exactly those powers (one multiplication
+ * per element), larger boundaries use two sqrt(n)-entry tables (two multiplications).  Default 20
+ * (32 MB, L2-resident).  0 forces the two-table form everywhere (tests pin that path at small
+ * sizes).  Cached twiddle tables are dropped. */
+int b200zk_ntt_tune(uint32_t direct_twiddle_max_log_n);
 /* Number of kernels launched by this library since init (for bench.py gpu_launches). */
 uint64_t b200zk_kernel_launches(void);
 

@@ -508,30 +508,71 @@ void orc_gen_scalars(uint64_t* out, size_t n, uint64_t seed, size_t start) {
         if (geq_p(l, FR.p)) sub_p(l, FR.p);
     }
 }
+/* P_i = [t_i] G with t_i = splitmix64(seed<<32 + i) | 1: byte-window tables tbl[j][b] = [b * 2^(8j)] G
+ * (8 mixed additions per point) and one field inversion per 256 points (Montgomery's trick) for the
+ * affine form.  The points are unique group elements in unique affine form, so the table layout does
+ * not show in the output (tests/test_oracle.py pins them against oracle/bn254.py). */
 typedef struct { uint64_t* out; size_t lo, hi, start; uint64_t seed; const g1a* tbl; } gen_job;
+#define GEN_BATCH 256
 static void* gen_points_thread(void* arg) {
     gen_job* j = (gen_job*)arg;
-    for (size_t i = j->lo; i < j->hi; ++i) {
-        uint64_t t = splitmix64((j->seed << 32) + (j->start + i)) | 1ull;
-        g1j acc;
-        g1j_set_id(&acc);
-        for (int b = 0; b < 64; ++b)
-            if ((t >> b) & 1) g1j_add_affine(&acc, &acc, &j->tbl[b]);
-        g1j_to_affine((g1a*)(j->out + 8 * i), &acc);
+    g1j acc[GEN_BATCH];
+    fe pre[GEN_BATCH];
+    for (size_t i0 = j->lo; i0 < j->hi; i0 += GEN_BATCH) {
+        size_t m = j->hi - i0 < GEN_BATCH ? j->hi - i0 : GEN_BATCH;
+        fe run = FQ.one;
+        for (size_t u = 0; u < m; ++u) {
+            uint64_t t = splitmix64((j->seed << 32) + (j->start + i0 + u)) | 1ull;
+            g1j_set_id(&acc[u]);
+            for (int b = 0; b < 8; ++b) {
+                unsigned d = (unsigned)(t >> (8 * b)) & 255u;
+                if (d) g1j_add_affine(&acc[u], &acc[u], &j->tbl[b * 256 + d]);
+            }
+            pre[u] = run;                      /* product of the z of the earlier points of the batch */
+            if (!fe_is_zero(&acc[u].z)) f_mul(&FQ, &run, &run, &acc[u].z);
+        }
+        fe inv;
+        f_inv(&FQ, &inv, &run);
+        for (size_t u = m; u-- > 0;) {
+            g1a* o = (g1a*)(j->out + 8 * (i0 + u));
+            if (fe_is_zero(&acc[u].z)) { memset(o, 0, sizeof *o); continue; }
+            fe zi, zi2, zi3;
+            f_mul(&FQ, &zi, &inv, &pre[u]);
+            f_mul(&FQ, &inv, &inv, &acc[u].z);
+            f_sqr(&FQ, &zi2, &zi);
+            f_mul(&FQ, &zi3, &zi2, &zi);
+            f_mul(&FQ, &o->x, &acc[u].x, &zi2);
+            f_mul(&FQ, &o->y, &acc[u].y, &zi3);
+        }
     }
     return NULL;
 }
 /* oracle/bn254.py seeded_g1_points: P_i = [splitmix64(seed<<32 + i) | 1] G, G = (1, 2) */
 void orc_gen_points(uint64_t* out, size_t n, uint64_t seed, size_t start, int threads) {
-    g1a tbl[64];
-    g1j p;
-    p.x = FQ.one;
-    f_dbl(&FQ, &p.y, &FQ.one);
-    p.z = FQ.one;
-    for (int b = 0; b < 64; ++b) {
-        g1j_to_affine(&tbl[b], &p);
-        g1j_double(&p, &p);
+    static g1a tbl[8 * 256];
+    static int tbl_ready = 0;
+    static pthread_mutex_t tbl_mu = PTHREAD_MUTEX_INITIALIZER;
+    pthread_mutex_lock(&tbl_mu);
+    if (!tbl_ready) {
+        g1j base;
+        base.x = FQ.one;
+        f_dbl(&FQ, &base.y, &FQ.one);
+        base.z = FQ.one;
+        for (int b = 0; b < 8; ++b) {
+            g1a step;
+            g1j_to_affine(&step, &base);       /* [2^(8b)] G */
+            g1j acc;
+            g1j_set_id(&acc);
+            memset(&tbl[b * 256], 0, sizeof(g1a));
+            for (int d = 1; d < 256; ++d) {
+                g1j_add_affine(&acc, &acc, &step);
+                g1j_to_affine(&tbl[b * 256 + d], &acc);
+            }
+            for (int q = 0; q < 8; ++q) g1j_double(&base, &base);
+        }
+        tbl_ready = 1;
     }
+    pthread_mutex_unlock(&tbl_mu);
     if (threads < 1) threads = 1;
     if (threads > 64) threads = 64;
     pthread_t th[64];

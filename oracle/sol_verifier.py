@@ -232,7 +232,7 @@ def _verify(evm: _Evm) -> bool:
     def mulmod(a, b, m): return (a * b) % m
     def sub(a, b): return (a - b) % W
 
-    # contract.sol:74-88
+    # contract.sol:73-87
     def read_ec_point(success, proof_cptr, hash_mptr):
         x = calldataload(proof_cptr)
         y = calldataload(proof_cptr + 0x20)
@@ -243,7 +243,7 @@ def _verify(evm: _Evm) -> bool:
         mstore(hash_mptr + 0x20, y)
         return ret0, proof_cptr + 0x40, hash_mptr + 0x40
 
-    # contract.sol:90-99
+    # contract.sol:89-99
     def squeeze_challenge(challenge_mptr, hash_mptr):
         h = evm.keccak256(0x00, hash_mptr)
         mstore(challenge_mptr, h % r)
@@ -258,7 +258,7 @@ def _verify(evm: _Evm) -> bool:
         mstore(0x00, h)
         return challenge_mptr + 0x20
 
-    # contract.sol:114-157
+    # contract.sol:114-159
     def batch_invert(success, mptr_start, mptr_end):
         gp_mptr = mptr_end
         gp = mload(mptr_start)
@@ -292,7 +292,7 @@ def _verify(evm: _Evm) -> bool:
         mstore(second_mptr, inv_second)
         return ret
 
-    # contract.sol:159-195
+    # contract.sol:161-188
     def ec_add_acc(success, x, y):
         mstore(0x40, x)
         mstore(0x60, y)
@@ -311,7 +311,7 @@ def _verify(evm: _Evm) -> bool:
         mstore(0xc0, scalar)
         return success and bool(evm.staticcall(0x07, 0x80, 0x60, 0x80, 0x40))
 
-    # contract.sol:197-214
+    # contract.sol:190-207
     def ec_pairing(success, lhs_x, lhs_y, rhs_x, rhs_y):
         mstore(0x00, lhs_x)
         mstore(0x20, lhs_y)
@@ -330,7 +330,7 @@ def _verify(evm: _Evm) -> bool:
 
     success = True
 
-    # ---- contract.sol:221-352: transcript, challenges, calldata checks
+    # ---- contract.sol:216-352: transcript, challenges, calldata checks
     evm.extcodecopy(VK_MPTR, 0x00, 0x40)
     success = success and calldataload(PROOF_LEN_CPTR) == PROOF_LEN
     num_instances = mload(NUM_INSTANCES_MPTR)
@@ -523,7 +523,7 @@ def _verify(evm: _Evm) -> bool:
     left_sub_right = addmod(lhs, sub(r, rhs), r)
     ev = addmod(left_sub_right, sub(r, mulmod(left_sub_right, addmod(mload(L_LAST_MPTR), mload(L_BLIND_MPTR), r), r)), r)
     quotient_eval_numer = addmod(mulmod(quotient_eval_numer, y, r), ev, r)
-    quotient_eval = mulmod(quotient_eval_numer, mload(X_N_MINUS_1_INV_MPTR), r)      # :512-513
+    quotient_eval = mulmod(quotient_eval_numer, mload(X_N_MINUS_1_INV_MPTR), r)      # :510-511
     mstore(QUOTIENT_EVAL_MPTR, quotient_eval)
 
     # ---- contract.sol:516-534: h = h_0 + x^n h_1 (Horner from the last piece)
@@ -550,7 +550,7 @@ def _verify(evm: _Evm) -> bool:
     for _ in range(5):
         x_pow_of_omega = mulmod(x_pow_of_omega, omega_inv, r)
     mstore(0x0280, x_pow_of_omega)
-    # :554-580  mu - point_i, the set vanishing value and the set differences
+    # :552-580  mu - point_i, the set vanishing value and the set differences
     mu = mload(MU_MPTR)
     mptr, mptr_end, point_mptr = 0x02e0, 0x0340, 0x0280
     while mptr < mptr_end:
@@ -641,7 +641,7 @@ def _verify(evm: _Evm) -> bool:
     total = mload(0xa0)
     total = addmod(total, mload(0xc0), r)
     mstore(0x0460, total)
-    # :698-727
+    # :698-729
     mptr, mptr_end, sum_mptr = 0x00, 0x60, 0x0420
     while mptr < mptr_end:
         mstore(mptr, mload(sum_mptr))
@@ -656,7 +656,7 @@ def _verify(evm: _Evm) -> bool:
         sum_inv_mptr = sub(sum_inv_mptr, 0x20)
         r_eval_mptr = sub(r_eval_mptr, 0x20)
     mstore(G1_SCALAR_MPTR, sub(r, r_eval))
-    # :728-779  the left-hand side of the pairing
+    # :731-779  the left-hand side of the pairing
     zeta = mload(ZETA_MPTR)
     nu = mload(NU_MPTR)
     mstore(0x00, calldataload(0x01c4))

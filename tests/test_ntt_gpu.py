@@ -29,6 +29,48 @@ def test_best_fft_vs_oracle(zk, k):
     assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("k", [21, 22, 23, 24, 25])
+def test_best_fft_vs_oracle_at_benchmark_sizes(zk, k):
+    """The headline sizes, bit for bit against the C restatement: three passes (7+7+7 ... 9+8+8), the first
+    boundary on the lo / hi two-multiplication twiddle path that only exists above 2^20, and from 2^22 the
+    host-buffer transfer pipeline (first and last pass in column ranges around chunked copies).  Both the
+    host-pointer call and the device-resident one."""
+    import torch
+
+    lib = zk.load()
+    n = 1 << k
+    a = co.gen_scalars(0xA11CE000 + k, n)
+    w = omega_for(k)
+    exp = co.best_fft(a, fr1(w), k)
+    dev = torch.from_numpy(a.view(np.int64).reshape(-1)).cuda()
+    zk.check(lib.b200zk_ntt_dev(C.c_void_p(dev.data_ptr()), n, 1, k, C.c_void_p(fr1(w).ctypes.data), None, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy().view(np.uint64).reshape(n, 4), exp)
+    del dev
+    got = a.copy()
+    zk.best_fft(got, w, k)
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("k", [2, 5, 9, 10, 13, 16, 18, 19, 20])
+def test_best_fft_two_table_twiddles_forced(zk, k):
+    """b200zk_ntt_tune(0): every pass boundary takes the lo / hi table form (two multiplications) that
+    the large transforms use for their first boundary; pinned here by the oracle at the small sizes, for
+    the forward transform and the fused-divisor inverse."""
+    lib = zk.load()
+    a = co.gen_scalars(0xA11CE000 + k, 1 << k)
+    w = omega_for(k)
+    try:
+        zk.check(lib.b200zk_ntt_tune(0))
+        got = a.copy()
+        zk.best_fft(got, w, k)
+        assert np.array_equal(got, co.best_fft(a, fr1(w), k))
+        d = zk.EvaluationDomain(3, k)
+        assert np.array_equal(d.lagrange_to_coeff(got.copy()), a)
+    finally:
+        zk.check(lib.b200zk_ntt_tune(20))
+
+
 def test_best_fft_edge_inputs(zk):
     k = 11
     n = 1 << k
