@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     ParamsKZG,
     best_fft,
     best_multiexp,
+    fresh,
     g1_affine_from_bytes,
     g1_affine_to_bytes,
     g1_sum,

@@ -110,6 +110,10 @@ def load() -> C.CDLL:
         "b200zk_msm_upload_pipeline": ([u32, sz], C.c_int),
         "b200zk_ntt_transfer_pipeline": ([u32, u32], C.c_int),
         "b200zk_ntt_tune": ([u32], C.c_int),
+        "b200zk_stream_release": ([vp], C.c_int),
+        "b200zk_mirror_enable": ([sz], C.c_int),
+        "b200zk_mirror_invalidate": ([vp, sz], C.c_int),
+        "b200zk_mirror_stats": ([u64p], C.c_int),
         "b200zk_msm_last_stages": ([C.POINTER(C.c_float), C.c_int, u64p], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():

@@ -47,6 +47,14 @@ def _check_vec(a, width: int, name: str) -> np.ndarray:
     return a
 
 
+def fresh(a: np.ndarray) -> np.ndarray:
+    """A newly allocated host buffer about to be handed to the library: no device mirror of an earlier
+    buffer at the same address may survive (the contract of b200zk_mirror_enable; the Rust fork does
+    this in `Polynomial`'s `Drop`).  A no-op while mirrors are off."""
+    check(load().b200zk_mirror_invalidate(C.c_void_p(a.ctypes.data), a.nbytes))
+    return a
+
+
 def init(device: int = -1) -> None:
     check(load().b200zk_init(device))
 
@@ -175,7 +183,7 @@ class EvaluationDomain:
     def lagrange_to_coeff(self, a: np.ndarray) -> np.ndarray:
         _check_vec(a, 4, "a")
         assert a.shape[0] == self.n
-        out = a.copy()
+        out = fresh(a.copy())
         check(load().b200zk_intt(_ptr(out), self.k, _ptr(self.omega_inv), _ptr(self.ifft_divisor)))
         return out
 
@@ -190,7 +198,7 @@ class EvaluationDomain:
     def coeff_to_extended(self, a: np.ndarray) -> np.ndarray:
         _check_vec(a, 4, "a")
         assert a.shape[0] == self.n
-        out = np.zeros((self.extended_len(), 4), dtype=np.uint64)
+        out = fresh(np.zeros((self.extended_len(), 4), dtype=np.uint64))
         check(load().b200zk_coeff_to_extended(_ptr(a), self.k, _ptr(out), self.extended_k,
                                               _ptr(self.extended_omega), _ptr(self.g_coset)))
         return out
@@ -208,7 +216,7 @@ class EvaluationDomain:
         _check_vec(a, 4, "a")
         assert a.shape[0] == self.extended_len()
         keep = self.n * self.quotient_poly_degree
-        out = np.zeros((keep, 4), dtype=np.uint64)
+        out = fresh(np.zeros((keep, 4), dtype=np.uint64))
         check(load().b200zk_extended_to_coeff(_ptr(a), self.extended_k, _ptr(self.extended_omega_inv),
                                               _ptr(self.extended_ifft_divisor), _ptr(self.g_coset), _ptr(out),
                                               keep))
@@ -217,7 +225,7 @@ class EvaluationDomain:
     def divide_by_vanishing_poly(self, h: np.ndarray) -> np.ndarray:
         _check_vec(h, 4, "h")
         assert h.shape[0] == self.extended_len()
-        out = h.copy()
+        out = fresh(h.copy())
         check(load().b200zk_divide_by_vanishing(_ptr(out), self.extended_k, _ptr(self.t_evaluations),
                                                 self.t_evaluations.shape[0]))
         return out

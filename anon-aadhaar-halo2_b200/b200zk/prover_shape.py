@@ -246,6 +246,132 @@ class ProverHotPath:
         t["total"] = sum(t.values())
         return t
 
+    # ------------------------------------------------------------ the same proof, one host-pointer call at a time
+    # What an *untouched* `create_proof` does through the patched halo2_proofs bodies
+    # (rust/halo2_proofs_patch/arithmetic_patch.rs): every polynomial is a host `Vec<Fr>`, every call is
+    # synchronous and takes / returns host memory.  Call sequence:
+    #   commit_lagrange(p) for every advice / permuted / product column          b200zk_msm_g1_registered
+    #   lagrange_to_coeff(p) for each of them                                     b200zk_intt
+    #   coeff_to_extended(z) for the permutation products (kept by `Committed`)   b200zk_coeff_to_extended
+    #   evaluate_h(pk, advice, instance, .., lookups, permutations)               its replaced body: uploads of the
+    #       coefficient columns and product cosets it is handed, device transforms + quotient kernels, one download
+    #   divide_by_vanishing_poly, extended_to_coeff, commit(h piece) x (d - 1)    the host-pointer calls
+    # With `mirror=True` the library keeps device mirrors of the host polynomials (b200zk_mirror_enable), so a
+    # polynomial is uploaded by the first call that sees it and found in HBM by the later ones.
+    def prepare_percall(self, pinned: bool = True) -> None:
+        s, n, N = self.shape, self.n, self.N
+        alloc = host_alloc_fr if pinned else (lambda count: np.zeros((count, 4), dtype=np.uint64))
+        self._percall_pinned = pinned
+        self.h_lag = alloc(self.n_lag * n)
+        self.h_instance = alloc(s.instance * n)
+        self.h_prod_ext = alloc(s.permutation_sets * N)
+        self.h_values = alloc(N)
+        self.h_hcoeff = alloc(n * (s.degree - 1))
+        self.h_points = np.zeros((self.n_lag + s.degree - 1, 12), dtype=np.uint64)
+
+    def run_percall(self, mirror: bool = False, mirror_bytes: int = 8 << 30) -> dict:
+        lib, s, d, n, N = self.lib, self.shape, self.domain, self.n, self.N
+        if not hasattr(self, "h_lag"):
+            self.prepare_percall()
+        t = {}
+        marks = [time.perf_counter()]
+
+        def mark(name):
+            marks.append(time.perf_counter())          # every call below is synchronous
+            t[name] = 1e3 * (marks[-1] - marks[-2])
+
+        # fresh witness-shaped columns on the host (not timed: stands in for synthesis)
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.lag.ptr), self.lag.n, self.seed + 2, 0))
+        check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.instance_coeff.ptr), self.instance_coeff.n, self.seed + 3, 0))
+        check(lib.b200zk_dev_download(self.lag.handle, 0, _ptr(self.h_lag), self.lag.n))
+        check(lib.b200zk_dev_download(self.instance_coeff.handle, 0, _ptr(self.h_instance), self.instance_coeff.n))
+        check(lib.b200zk_mirror_enable(0))             # no mirror survives from the set-up above
+        if mirror:
+            check(lib.b200zk_mirror_enable(mirror_bytes))
+        col = lambda a, c, width: C.c_void_p(a.ctypes.data + c * width * 32)
+        pp0 = s.advice + 2 * s.lookups
+        lp0 = pp0 + s.permutation_sets
+        self.sync()
+        marks[0] = time.perf_counter()
+        # ---- ParamsKZG::commit_lagrange, one polynomial per call
+        for c in range(self.n_lag):
+            check(lib.b200zk_msm_g1_registered(self.h_bases, col(self.h_lag, c, n), n, _ptr(self.h_points[c])))
+        mark("commit_lagrange")
+        # ---- EvaluationDomain::lagrange_to_coeff, in place on each host polynomial
+        for c in range(self.n_lag):
+            check(lib.b200zk_intt(col(self.h_lag, c, n), d.k, _ptr(d.omega_inv), _ptr(d.ifft_divisor)))
+        mark("lagrange_to_coeff")
+        # ---- permutation::Argument::commit keeps the extended form of every product polynomial
+        for i in range(s.permutation_sets):
+            check(lib.b200zk_coeff_to_extended(col(self.h_lag, pp0 + i, n), d.k, col(self.h_prod_ext, i, N), d.extended_k,
+                                               _ptr(d.extended_omega), _ptr(d.g_coset)))
+        mark("coeff_to_extended_products")
+        # ---- Evaluator::evaluate_h (replaced body): stage what it is handed, extend, evaluate, return one column
+        for c in list(range(pp0)) + list(range(lp0, self.n_lag)):
+            check(lib.b200zk_dev_upload(self.lag.handle, c * n, col(self.h_lag, c, n), n))
+        for c in range(s.instance):
+            check(lib.b200zk_dev_upload(self.instance_coeff.handle, c * n, col(self.h_instance, c, n), n))
+        for i in range(s.permutation_sets):
+            check(lib.b200zk_dev_upload(self.ext.handle, (pp0 + i) * N, col(self.h_prod_ext, i, N), N))
+        for first, count in ((0, pp0), (lp0, self.n_lag - lp0)):
+            check(lib.b200zk_coeff_to_extended_dev(C.c_void_p(self.lag.ptr + first * n * 32), n,
+                                                   C.c_void_p(self.ext.ptr + first * N * 32), N, count, d.k, d.extended_k,
+                                                   _ptr(d.extended_omega), _ptr(d.g_coset), None))
+        check(lib.b200zk_coeff_to_extended_dev(C.c_void_p(self.instance_coeff.ptr), n,
+                                               C.c_void_p(self.ext.ptr + self.n_lag * N * 32), N, s.instance, d.k,
+                                               d.extended_k, _ptr(d.extended_omega), _ptr(d.g_coset), None))
+        self._quotient_kernels()
+        check(lib.b200zk_dev_download(self.values.handle, 0, _ptr(self.h_values), N))
+        mark("evaluate_h")
+        # ---- vanishing::Argument::construct
+        check(lib.b200zk_divide_by_vanishing(_ptr(self.h_values), d.extended_k, _ptr(d.t_evaluations),
+                                             d.t_evaluations.shape[0]))
+        keep = n * (s.degree - 1)
+        check(lib.b200zk_extended_to_coeff(_ptr(self.h_values), d.extended_k, _ptr(d.extended_omega_inv),
+                                           _ptr(d.extended_ifft_divisor), _ptr(d.g_coset), _ptr(self.h_hcoeff), keep))
+        mark("divide_and_extended_to_coeff")
+        for j in range(s.degree - 1):
+            check(lib.b200zk_msm_g1_registered(self.h_bases, col(self.h_hcoeff, j, n), n, _ptr(self.h_points[self.n_lag + j])))
+        mark("commit_h_pieces")
+        t["total"] = 1e3 * (marks[-1] - marks[0])
+        if mirror:
+            st = (C.c_uint64 * 4)()
+            check(lib.b200zk_mirror_stats(st))
+            self.mirror_stats = {"hits": int(st[0]), "misses": int(st[1]), "resident_bytes": int(st[2]), "evictions": int(st[3])}
+            check(lib.b200zk_mirror_enable(0))
+        return t
+
+    def percall_counts(self) -> dict:
+        s = self.shape
+        return {"b200zk_msm_g1_registered": self.n_lag + s.degree - 1, "b200zk_intt": self.n_lag,
+                "b200zk_coeff_to_extended": s.permutation_sets,
+                "b200zk_dev_upload (inside evaluate_h)": self.n_lag + s.instance,
+                "b200zk_divide_by_vanishing": 1, "b200zk_extended_to_coeff": 1}
+
+    def _quotient_kernels(self) -> None:
+        """The gate, permutation and lookup blocks of evaluate_h over the extended columns (as in run())."""
+        lib, s, d = self.lib, self.shape, self.domain
+        env = self._env()
+        g = self.gates.as_c()
+        check(lib.b200zk_quotient_graph(C.byref(g), C.byref(env), 0, self.values.handle))
+        lk0 = s.advice
+        pp0 = s.advice + 2 * s.lookups
+        lp0 = pp0 + s.permutation_sets
+        products = self.ext_views[pp0: pp0 + s.permutation_sets]
+        sig, ph = _handles(self.sigma), _handles(products)
+        zeta, delta = fr_limbs(FR_ZETA), fr_limbs(FR_DELTA)
+        check(lib.b200zk_quotient_permutation(
+            C.byref(env), self.values.handle, _ptr32(self.perm_kind), _ptr32(self.perm_index), _ptr(sig),
+            len(self.perm_kind), _ptr(ph), len(products), s.degree - 2, s.blinding_factors, self.l0.handle,
+            self.l_last.handle, self.l_active.handle, _ptr(d.extended_omega), _ptr(zeta), _ptr(delta)))
+        for j in range(s.lookups):
+            lg = self.lookup_graphs[j].as_c()
+            check(lib.b200zk_quotient_graph(C.byref(lg), C.byref(env), 0, self.table.handle))
+            check(lib.b200zk_quotient_lookup(C.byref(env), self.values.handle, self.table.handle,
+                                             self.ext_views[lp0 + j].handle, self.ext_views[lk0 + 2 * j].handle,
+                                             self.ext_views[lk0 + 2 * j + 1].handle, self.l0.handle,
+                                             self.l_last.handle, self.l_active.handle))
+
     # ------------------------------------------------------------ the same proof with the phases overlapped
     def run_overlapped(self, torch, hi_stream, lo_stream) -> dict:
         """The stages of run() as a prover that owns both sides would issue them: the commitments on a
@@ -474,6 +600,10 @@ class ProverHotPath:
         if getattr(self, "host_advice", None) is not None:
             host_free(self.host_advice)
             self.host_advice = None
+        if getattr(self, "_percall_pinned", False):
+            for name in ("h_lag", "h_instance", "h_prod_ext", "h_values", "h_hcoeff"):
+                host_free(getattr(self, name))
+            self._percall_pinned = False
         for v in self.ext_views + self.fixed + self.sigma + [self.l0, self.l_last, self.l_active]:
             v.free()
         for q, (col, views) in getattr(self, "pk_coset", {}).items():

@@ -160,13 +160,12 @@ int b200zk_shutdown(void) {
         cudaStreamSynchronize(c.stream);
         ntt_release_tables(c);
         msm_release_bases(c);
-        for (Arena* a : {&c.ntt_io, &c.ntt_tmp, &c.ntt_aux, &c.msm_scalars, &c.msm_bases, &c.msm_work, &c.msm_carry, &c.misc, &c.quot_graph, &c.quot_ptrs,
-                         &c.poly_work, &c.poly_small, &c.poly_cols, &c.poly_scan, &c.enc_io})
-            a->release();
+        c.release_scratch();
+        c.mirrors.release();
+        c.mirrors.enabled = false;
         for (auto& kv : c.buffers)
             if (kv.second.owned) cudaFree(kv.second.p);
         c.buffers.clear();
-        c.pinned.release();
         for (void* p : g_host_registered) cudaHostUnregister(p);
         for (void* p : g_host_allocated) cudaFreeHost(p);
         g_host_registered.clear();
@@ -178,6 +177,58 @@ int b200zk_shutdown(void) {
 }
 
 uint64_t b200zk_kernel_launches(void) { return g_launches.load(); }
+
+int b200zk_mirror_enable(size_t max_bytes) {
+    return guarded([&] {
+        Context& c = ctx();
+        if (max_bytes == 0) {
+            if (c.ready) {
+                ZK_CUDA(cudaSetDevice(c.device));
+                ZK_CUDA(cudaDeviceSynchronize());
+            }
+            c.mirrors.release();
+            c.mirrors.enabled = false;
+            c.mirrors.max_bytes = 0;
+            return;
+        }
+        ensure_init();
+        c.mirrors.enabled = true;
+        c.mirrors.max_bytes = max_bytes;
+    });
+}
+
+int b200zk_mirror_invalidate(const void* host_ptr, size_t bytes) {
+    return guarded([&] {
+        Context& c = ctx();
+        if (!c.mirrors.enabled || !host_ptr) return;
+        // the library stream may still be reading the mirror (host-pointer calls are synchronous, so it is
+        // idle here); freed blocks are only ever reused by work queued later on that stream
+        c.mirrors.invalidate(host_ptr, bytes);
+    });
+}
+
+int b200zk_mirror_stats(uint64_t out[4]) {
+    return guarded([&] {
+        ZK_REQUIRE(out, "null argument");
+        Context& c = ctx();
+        out[0] = c.mirrors.hits; out[1] = c.mirrors.misses; out[2] = c.mirrors.resident_bytes; out[3] = c.mirrors.evictions;
+    });
+}
+
+int b200zk_stream_release(void* stream) {
+    return guarded([&] {
+        Context& c = ctx();
+        if (!c.ready) return;
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        auto it = c.scratch_sets.find(s);
+        if (it == c.scratch_sets.end()) return;
+        ZK_CUDA(cudaSetDevice(c.device));
+        ZK_CUDA(cudaDeviceSynchronize());
+        it->second->release();
+        delete it->second;
+        c.scratch_sets.erase(it);
+    });
+}
 
 int b200zk_host_register(void* ptr, size_t bytes) {
     return guarded([&] {
@@ -234,7 +285,7 @@ int b200zk_gen_points_dev(void* d_out, size_t n, uint64_t seed, size_t start) {
         ensure_init();
         if (n == 0) return;
         Context& c = ctx();
-        G1Affine* tbl = (G1Affine*)c.misc.get(64 * sizeof(G1Affine));
+        G1Affine* tbl = (G1Affine*)c.scratch(c.stream).misc.get(64 * sizeof(G1Affine));
         gen_pow2_table_kernel<<<1, 32, 0, c.stream>>>(tbl);
         ZK_LAUNCH_CHECK();
         gen_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>((G1Affine*)d_out, n, seed, start, tbl);
@@ -248,7 +299,7 @@ int b200zk_modmul_peak(uint32_t iters, double* modmul_per_s_out) {
         ensure_init();
         Context& c = ctx();
         const int blocks = c.sm_count * 8, threads = 256;
-        Fq* sink = (Fq*)c.misc.get((size_t)blocks * threads * sizeof(Fq));
+        Fq* sink = (Fq*)c.scratch(c.stream).misc.get((size_t)blocks * threads * sizeof(Fq));
         cudaEvent_t e0, e1;
         ZK_CUDA(cudaEventCreate(&e0));
         ZK_CUDA(cudaEventCreate(&e1));

@@ -152,7 +152,7 @@ static void encode(const uint64_t* pts, size_t count, int is_affine, int mode, u
     Context& c = ctx();
     cudaStream_t s = c.stream;
     const size_t in_bytes = count * (is_affine ? 64 : 96), out_bytes = count * (mode ? 64 : 32);
-    char* d = (char*)c.enc_io.get(in_bytes + out_bytes + 256);
+    char* d = (char*)c.scratch(s).enc_io.get(in_bytes + out_bytes + 256);
     char* dout = d + (in_bytes + 255) / 256 * 256;
     ZK_CUDA(cudaMemcpyAsync(d, pts, in_bytes, cudaMemcpyHostToDevice, s));
     g1_encode_kernel<<<(unsigned)((count + 127) / 128), 128, 0, s>>>((const Fq*)d, (uint32_t)count, is_affine, mode,
@@ -189,7 +189,7 @@ int b200zk_g1_affine_from_bytes(const uint8_t* in32, size_t count, uint64_t* poi
         Context& c = ctx();
         cudaStream_t s = c.stream;
         const size_t in_bytes = (count * 32 + 255) / 256 * 256, out_bytes = (count * 64 + 255) / 256 * 256;
-        char* d = (char*)c.enc_io.get(in_bytes + out_bytes + count * 4);
+        char* d = (char*)c.scratch(s).enc_io.get(in_bytes + out_bytes + count * 4);
         uint8_t* din = (uint8_t*)d;
         Fq* dout = (Fq*)(d + in_bytes);
         uint32_t* dst = (uint32_t*)(d + in_bytes + out_bytes);

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 
 namespace zk {
 
@@ -45,8 +46,10 @@ struct BaseTable {
 
 static void msm_release_pipeline();
 
+static void msm_release_stage_events();
 void msm_release_bases(Context& c) {
     msm_release_pipeline();
+    msm_release_stage_events();
     for (auto& kv : c.bases) {
         cudaFree(kv.second->d);
         if (kv.second->table) cudaFree(kv.second->table);
@@ -234,9 +237,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint32_t* bsum,
     if (threadIdx.x == 0) *total_out = running;
 }
 
+// What the pair count decides, computed on the device so that the host never has to wait for it:
+// the accumulation's chunk length and thread count and the entry count of every keyed-reduction
+// level.  The host launches grids for the worst case; threads beyond the planned counts exit.
+constexpr int MSM_MAX_LEVELS = 12;
+struct MsmRun {
+    uint32_t npairs, L, nthreads, pad;
+    uint32_t level_count[MSM_MAX_LEVELS];   // entries entering combine level l
+};
+
 __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __restrict__ out, uint32_t* __restrict__ copy,
                                                                 const uint32_t* __restrict__ bsum, size_t n,
-                                                                const uint32_t* __restrict__ total) {
+                                                                const uint32_t* __restrict__ total, uint32_t chunk_unit,
+                                                                uint32_t max_chunk, MsmRun* __restrict__ run) {
     const size_t base = (size_t)blockIdx.x * SCAN_BLOCK + (size_t)threadIdx.x * SCAN_ITEMS;
     const uint32_t add = bsum[blockIdx.x];
 #pragma unroll
@@ -247,7 +260,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __rest
             copy[base + i] = v;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;  // start[K] = number of pairs
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint32_t np = *total;
+        out[n] = np;  // start[K] = number of pairs
+        // chunk length: keep >= chunk_unit threads queued, between 4 and max_chunk pairs each
+        const uint32_t L = min(max_chunk, max(4u, np / chunk_unit));
+        run->npairs = np;
+        run->L = L;
+        run->nthreads = (np + L - 1) / L;
+        run->level_count[0] = run->nthreads;
+    }
 }
 
 // --------------------------------------------------------------------- 3. scatter
@@ -306,12 +328,12 @@ __device__ __forceinline__ uint32_t find_key(const uint32_t* __restrict__ start,
 // continues from what the earlier ranges left in the bucket.
 template <bool ADD>
 __global__ void __launch_bounds__(128, 5) msm_accum_kernel(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                        const uint32_t* __restrict__ start, uint32_t nkeys, uint32_t npairs,
-                                                        uint32_t L, G1Xyzz* __restrict__ buckets,
-                                                        uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt,
-                                                        uint32_t nthreads) {
+                                                        const uint32_t* __restrict__ start, uint32_t nkeys,
+                                                        const MsmRun* __restrict__ run, G1Xyzz* __restrict__ buckets,
+                                                        uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nthreads) return;
+    const uint32_t npairs = __ldg(&run->npairs), L = __ldg(&run->L);
+    if (t >= __ldg(&run->nthreads)) return;
     const uint32_t begin = t * L;
     const uint32_t end = min(begin + L, npairs);
     uint32_t key = find_key(start, nkeys, begin);
@@ -363,10 +385,13 @@ __global__ void __launch_bounds__(128, 5) msm_accum_kernel(const G1Affine* __res
 //
 // Sequential form (throughput regime): thread t owns entries [t*L, (t+1)*L).
 __global__ void __launch_bounds__(128) msm_combine_kernel(const uint32_t* __restrict__ keys, const G1Xyzz* __restrict__ pts,
-                                                          uint32_t count, uint32_t L, G1Xyzz* __restrict__ buckets,
-                                                          uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt,
-                                                          uint32_t nthreads) {
+                                                          MsmRun* __restrict__ run, uint32_t level, uint32_t L,
+                                                          G1Xyzz* __restrict__ buckets,
+                                                          uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = run->level_count[level];
+    const uint32_t nthreads = (count + L - 1) / L;
+    if (t == 0) run->level_count[level + 1] = nthreads;
     if (t >= nthreads) return;
     const uint32_t begin = t * L;
     const uint32_t end = min(begin + L, count);
@@ -414,11 +439,13 @@ __device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& v, uint32_t d) {
 // steps; each warp hands up one entry, so a level shrinks the list 32x for the latency of
 // five point additions.  When count <= 32 the single warp closes everything.
 __global__ void __launch_bounds__(128) msm_combine_warp_kernel(const uint32_t* __restrict__ keys,
-                                                               const G1Xyzz* __restrict__ pts, uint32_t count,
-                                                               G1Xyzz* __restrict__ buckets,
+                                                               const G1Xyzz* __restrict__ pts, MsmRun* __restrict__ run,
+                                                               uint32_t level, G1Xyzz* __restrict__ buckets,
                                                                uint32_t* __restrict__ carry_key,
                                                                G1Xyzz* __restrict__ carry_pt) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = run->level_count[level];
+    if (gid == 0) run->level_count[level + 1] = (count + 31) / 32;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = gid >> 5;
     const uint32_t base = warp << 5;
@@ -598,7 +625,6 @@ __global__ void g1_sum_kernel(const G1Jacobian* __restrict__ pts, uint32_t count
 enum MsmStage { MSM_ST_HIST = 0, MSM_ST_SCAN, MSM_ST_SCATTER, MSM_ST_SYNC, MSM_ST_ACCUM, MSM_ST_COMBINE,
                 MSM_ST_REDUCE, MSM_ST_REDUCE_COMBINE, MSM_ST_FOLD, MSM_ST_END, MSM_ST_COUNT };
 struct MsmInfo { uint64_t n; uint32_t c, nwin, npairs, chunk; };
-static MsmInfo g_msm_info = {0, 0, 0, 0, 0};
 static bool g_msm_profile = false;
 static uint32_t g_msm_max_chunk = 128;   // tunable (b200zk_msm_tune)
 static uint32_t g_msm_max_seglen = 64;    // measured: 104 -> 64 takes the 242-column reduce from 3.5 to 3.1 ms
@@ -617,28 +643,49 @@ static void msm_release_pipeline() {          // b200zk_shutdown: the next init 
     for (auto& e : g_msm_part_ev) cudaEventDestroy(e);
     g_msm_copy_stream = nullptr;
 }
+static void msm_release_stage_events();
 static uint32_t g_msm_chunk_div = getenv("B200ZK_MSM_CHUNK_DIV") ? (uint32_t)atoi(getenv("B200ZK_MSM_CHUNK_DIV")) : 2048u;
 static uint32_t g_msm_force_sub = getenv("B200ZK_MSM_SUB_BITS") ? (uint32_t)atoi(getenv("B200ZK_MSM_SUB_BITS")) : 0xffffffffu;
-static cudaEvent_t g_msm_ev[MSM_ST_COUNT];
-static bool g_msm_ev_made = false, g_msm_ev_valid[MSM_ST_COUNT];
+// stage events are kept per stream (a profiled MSM on one stream does not disturb another's);
+// b200zk_msm_last_stages reports the most recent profiled call
+struct MsmStageEvents {
+    cudaEvent_t ev[MSM_ST_COUNT];
+    bool valid[MSM_ST_COUNT];
+    MsmInfo info;
+    const MsmRun* d_run = nullptr;     // device plan of that call (pair count, chunk length)
+};
+static std::map<cudaStream_t, MsmStageEvents*> g_msm_stage_events;
+static MsmStageEvents* g_msm_last_profiled = nullptr;
 static cudaStream_t g_msm_ev_stream = nullptr;
+static void msm_release_stage_events() {
+    for (auto& kv : g_msm_stage_events) {
+        for (auto& e : kv.second->ev) cudaEventDestroy(e);
+        delete kv.second;
+    }
+    g_msm_stage_events.clear();
+    g_msm_last_profiled = nullptr;
+}
 
 struct StageTimer {
     cudaStream_t s;
     bool on;
+    MsmStageEvents* E = nullptr;
     StageTimer(Context&, cudaStream_t st) : s(st), on(g_msm_profile) {
         if (!on) return;
-        if (!g_msm_ev_made) {
-            for (int i = 0; i < MSM_ST_COUNT; ++i) ZK_CUDA(cudaEventCreate(&g_msm_ev[i]));
-            g_msm_ev_made = true;
-        }
-        for (int i = 0; i < MSM_ST_COUNT; ++i) g_msm_ev_valid[i] = false;
+        auto it = g_msm_stage_events.find(st);
+        if (it == g_msm_stage_events.end()) {
+            E = new MsmStageEvents();
+            for (int i = 0; i < MSM_ST_COUNT; ++i) ZK_CUDA(cudaEventCreate(&E->ev[i]));
+            g_msm_stage_events[st] = E;
+        } else E = it->second;
+        for (int i = 0; i < MSM_ST_COUNT; ++i) E->valid[i] = false;
         g_msm_ev_stream = st;
+        g_msm_last_profiled = E;
     }
     void mark(int stage) {
         if (!on) return;
-        ZK_CUDA(cudaEventRecord(g_msm_ev[stage], s));
-        g_msm_ev_valid[stage] = true;
+        ZK_CUDA(cudaEventRecord(E->ev[stage], s));
+        E->valid[stage] = true;
     }
 };
 
@@ -667,23 +714,26 @@ struct MsmPre {
 // added into `buckets`.  Small inputs use short chunks: the cost of a level is the latency
 // of L dependent point additions, not throughput.
 static void run_combine_levels(Context& c, uint32_t* keysA, G1Xyzz* ptsA, uint32_t* keysB, G1Xyzz* ptsB,
-                               uint32_t count, G1Xyzz* buckets, cudaStream_t s) {
+                               uint32_t count, MsmRun* run, G1Xyzz* buckets, cudaStream_t s) {
+    // `count` bounds the entries of level 0; the exact counts are in run->level_count (device)
+    uint32_t level = 0;
     while (count > 0) {
+        ZK_REQUIRE(level + 1 < (uint32_t)MSM_MAX_LEVELS, "too many keyed-reduction levels");
         if (count > 32768u) {
             // throughput regime: sequential chunks, one addition per entry
             const uint32_t L = count > (uint32_t)c.sm_count * 4096u ? 16u : 4u;
             const uint32_t nthreads = (count + L - 1) / L;
-            msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, count, L, buckets, keysB, ptsB,
-                                                                      nthreads);
+            msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, run, level, L, buckets, keysB, ptsB);
             ZK_LAUNCH_CHECK();
             count = nthreads;
         } else {
             const uint32_t nwarps = (count + 31) / 32;
-            msm_combine_warp_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, count, buckets, keysB, ptsB);
+            msm_combine_warp_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, run, level, buckets, keysB, ptsB);
             ZK_LAUNCH_CHECK();
             if (nwarps == 1) break;
             count = nwarps;
         }
+        ++level;
         std::swap(keysA, keysB);
         std::swap(ptsA, ptsB);
     }
@@ -770,14 +820,16 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     const size_t o_cursor = carve(((size_t)nkeys + 1) * 4);
     const size_t o_bsum = carve(((size_t)scan_blocks + 1) * 4);
     const size_t o_total = carve(256);
+    const size_t o_run = carve(sizeof(MsmRun));
     const size_t o_sorted = carve(max_pairs * 4);
     const size_t o_digits = carve(max_pairs * 4);
-    char* base = (char*)c.msm_work.get(off);
+    char* base = (char*)c.scratch(s).msm_work.get(off);
     uint32_t* hist = (uint32_t*)(base + o_hist);
     uint32_t* start = (uint32_t*)(base + o_start);
     uint32_t* cursor = (uint32_t*)(base + o_cursor);
     uint32_t* bsum = (uint32_t*)(base + o_bsum);
     uint32_t* total = (uint32_t*)(base + o_total);
+    MsmRun* run = (MsmRun*)(base + o_run);
     uint32_t* sorted = (uint32_t*)(base + o_sorted);
     int32_t* digits = (int32_t*)(base + o_digits);
     G1Xyzz* buckets = (G1Xyzz*)(base + o_buckets);
@@ -800,7 +852,12 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     ZK_LAUNCH_CHECK();
     scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(bsum, scan_blocks, total);
     ZK_LAUNCH_CHECK();
-    scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, nkeys, total);
+    // chunk length: keep >= ~2048 threads per SM queued, between 4 and 128 pairs each (longer
+    // chunks mean fewer open runs handed to the keyed-reduction levels; measured on B200 against
+    // 4096 / 1024 / 512: 1.79 -> 1.59 ms at 2^18, 4.27 -> 3.99 ms at 2^20, unchanged from 2^23 up).
+    // Chosen by the device from the pair count it has just produced (MsmRun).
+    const uint32_t chunk_unit = (uint32_t)c.sm_count * g_msm_chunk_div;
+    scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, nkeys, total, chunk_unit, g_msm_max_chunk, run);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SCATTER);
     // bucket sub-ranges: measured on B200 at k = 24, one split helps the shared-bucket (table)
@@ -811,16 +868,13 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
         digits, n, cbits, nwin, key_windows, pre ? (uint32_t)pre->n_reg : 0u, sub_bits, part.index_offset, cursor, sorted);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SYNC);
-    uint32_t npairs = 0;
-    ZK_CUDA(cudaMemcpyAsync(&npairs, total, 4, cudaMemcpyDeviceToHost, s));
-    ZK_CUDA(cudaStreamSynchronize(s));
-
-    // chunk length: keep >= ~2048 threads per SM queued, between 4 and 128 pairs each (longer
-    // chunks mean fewer open runs handed to the keyed-reduction levels; measured on B200 against
-    // 4096 / 1024 / 512: 1.79 -> 1.59 ms at 2^18, 4.27 -> 3.99 ms at 2^20, unchanged from 2^23 up)
-    const uint32_t L = (uint32_t)std::min<uint64_t>(g_msm_max_chunk, std::max<uint64_t>(4, npairs / ((uint64_t)c.sm_count * g_msm_chunk_div)));
-    const uint32_t nthreads0 = (npairs + L - 1) / L;
-    // ---- carve the carry arena now that the pair count is known
+    // No host round trip for the pair count: the accumulation is launched for the largest thread count any
+    // pair count <= max_pairs can plan (np / L(np) with L = clamp(np / chunk_unit, 4, max_chunk)).
+    const uint64_t bound_short = (max_pairs + 3) / 4;                                   // L = 4
+    const uint64_t bound_long = std::max<uint64_t>((uint64_t)chunk_unit * 5 / 4 + 2,   // 4 < L < max: np / floor(np / unit)
+                                                   max_pairs / g_msm_max_chunk + 1);     // L = max_chunk
+    const uint32_t nthreads0 = (uint32_t)std::max<uint64_t>(1, std::min(bound_short, bound_long));
+    // ---- carve the carry arena for that bound
     const size_t carry_cap = std::max<size_t>(std::max<size_t>(nthreads0, red_entries), 64);
     off = 0;
     const size_t o_keyA = carve(carry_cap * 4);
@@ -828,26 +882,27 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     const size_t capB = std::max<size_t>(carry_cap / 4 + 64, groups * 64);
     const size_t o_keyB = carve(capB * 4);
     const size_t o_ptB = carve(capB * sizeof(G1Xyzz));
-    char* cbase = (char*)c.msm_carry.get(off);
+    char* cbase = (char*)c.scratch(s).msm_carry.get(off);
     uint32_t* keyA = (uint32_t*)(cbase + o_keyA);
     G1Xyzz* ptA = (G1Xyzz*)(cbase + o_ptA);
     uint32_t* keyB = (uint32_t*)(cbase + o_keyB);
     G1Xyzz* ptB = (G1Xyzz*)(cbase + o_ptB);
-    g_msm_info.n = n * count; g_msm_info.c = cbits; g_msm_info.nwin = nwin; g_msm_info.npairs = npairs; g_msm_info.chunk = L;
+    if (T.on) {
+        T.E->info.n = n * count; T.E->info.c = cbits; T.E->info.nwin = nwin; T.E->info.npairs = 0; T.E->info.chunk = 0;
+        T.E->d_run = run;
+    }
 
     // ---- 4: accumulate
     T.mark(MSM_ST_ACCUM);
-    if (npairs > 0) {
-        if (part.first)
-            msm_accum_kernel<false><<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start,
-                                                                            nkeys, npairs, L, buckets, keyA, ptA, nthreads0);
-        else
-            msm_accum_kernel<true><<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start,
-                                                                           nkeys, npairs, L, buckets, keyA, ptA, nthreads0);
-        ZK_LAUNCH_CHECK();
-        T.mark(MSM_ST_COMBINE);
-        run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, buckets, s);
-    }
+    if (part.first)
+        msm_accum_kernel<false><<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start, nkeys, run,
+                                                                        buckets, keyA, ptA);
+    else
+        msm_accum_kernel<true><<<(nthreads0 + 127) / 128, 128, 0, s>>>(pre ? pre->table : d_bases, sorted, start, nkeys, run,
+                                                                       buckets, keyA, ptA);
+    ZK_LAUNCH_CHECK();
+    T.mark(MSM_ST_COMBINE);
+    run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, run, buckets, s);
 
     if (!part.last) {
         T.mark(MSM_ST_END);
@@ -899,9 +954,9 @@ int b200zk_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint
         ensure_init();
         Context& c = ctx();
         cudaStream_t s = c.stream;
-        Fr* ds = (Fr*)c.msm_scalars.get(std::max<size_t>(n, 1) * sizeof(Fr));
-        G1Affine* db = (G1Affine*)c.msm_bases.get(std::max<size_t>(n, 1) * sizeof(G1Affine));
-        G1Jacobian* dout = (G1Jacobian*)c.misc.get(sizeof(G1Jacobian));
+        Fr* ds = (Fr*)c.scratch(s).msm_scalars.get(std::max<size_t>(n, 1) * sizeof(Fr));
+        G1Affine* db = (G1Affine*)c.scratch(s).msm_bases.get(std::max<size_t>(n, 1) * sizeof(G1Affine));
+        G1Jacobian* dout = (G1Jacobian*)c.scratch(s).misc.get(sizeof(G1Jacobian));
         if (n) {
             ZK_CUDA(cudaMemcpyAsync(ds, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
             ZK_CUDA(cudaMemcpyAsync(db, bases, n * sizeof(G1Affine), cudaMemcpyHostToDevice, s));
@@ -922,7 +977,8 @@ static void register_bases(const uint64_t* bases, size_t n, int precompute, uint
         ZK_CUDA(cudaMemcpy(t->d, bases, n * sizeof(G1Affine), cudaMemcpyHostToDevice));
     }
     if (n && precompute) {
-        t->c = choose_window(n, true);
+        // precompute = 1: window size from the cost model; >= 4: that many bits (experiments, small-n tuning)
+        t->c = precompute >= 4 ? (uint32_t)std::min(precompute, 23) : choose_window(n, true);
         t->nwin = (255 + t->c - 1) / t->c;
         const size_t bytes = n * (size_t)t->nwin * sizeof(G1Affine);
         size_t free_b = 0, total_b = 0;
@@ -987,12 +1043,21 @@ static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stri
     ZK_REQUIRE(n <= t->n, "more scalars than registered bases");
     if (count == 0) return;
     cudaStream_t s = c.stream;
-    Fr* ds = (Fr*)c.msm_scalars.get(std::max<size_t>(n * count, 1) * sizeof(Fr));
-    G1Jacobian* dout = (G1Jacobian*)c.misc.get(count * sizeof(G1Jacobian));
+    // a single commit of a polynomial the library already mirrors (b200zk_mirror_enable) needs no upload
+    Fr* ds = nullptr;
+    bool resident = false;
+    if (count == 1 && n && c.mirrors.enabled) {
+        ds = (Fr*)c.mirrors.find(scalars, n);
+        resident = ds != nullptr;
+        if (!ds) ds = (Fr*)c.mirrors.insert(scalars, n);
+    } else {
+        ds = (Fr*)c.scratch(s).msm_scalars.get(std::max<size_t>(n * count, 1) * sizeof(Fr));
+    }
+    G1Jacobian* dout = (G1Jacobian*)c.scratch(s).misc.get(count * sizeof(G1Jacobian));
     MsmPre pre{t->table, t->n, t->c, t->nwin};
     // One large commit with a window table: feed it in point ranges that share the bucket set,
     // so the upload of range p+1 runs under the sort + accumulation of range p.
-    const size_t parts = (count == 1 && t->table && n >= g_msm_pipe_min_n) ? std::min<size_t>(g_msm_pipe_parts, MSM_MAX_PARTS) : 1;
+    const size_t parts = (count == 1 && !resident && t->table && n >= g_msm_pipe_min_n) ? std::min<size_t>(g_msm_pipe_parts, MSM_MAX_PARTS) : 1;
     if (parts > 1) {
         if (!g_msm_copy_stream) {
             ZK_CUDA(cudaStreamCreateWithFlags(&g_msm_copy_stream, cudaStreamNonBlocking));
@@ -1018,7 +1083,7 @@ static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stri
         ZK_CUDA(cudaStreamSynchronize(s));
         return;
     }
-    if (n)
+    if (n && !resident)
         ZK_CUDA(cudaMemcpy2DAsync(ds, n * sizeof(Fr), scalars, stride * sizeof(Fr), n * sizeof(Fr), count,
                                   cudaMemcpyHostToDevice, s));
     msm_device(c, ds, n, count, t->d, n, t->table ? &pre : nullptr, dout, s);
@@ -1058,7 +1123,7 @@ int b200zk_msm_g1_dev(const void* d_scalars, const void* d_bases, size_t n, uint
         ensure_init();
         Context& c = ctx();
         cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
-        G1Jacobian* dout = (G1Jacobian*)c.misc.get(sizeof(G1Jacobian));
+        G1Jacobian* dout = (G1Jacobian*)c.scratch(s).misc.get(sizeof(G1Jacobian));
         msm_device(c, (const Fr*)d_scalars, n, 1, (const G1Affine*)d_bases, n, nullptr, dout, s);
         copy_point_out(c, dout, out_xyz, s);
     });
@@ -1100,17 +1165,24 @@ int b200zk_msm_profile(int enable) {
 int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]) {
     return guarded([&] {
         ZK_REQUIRE(ms_out && capacity >= MSM_ST_COUNT - 1 && info_out, "bad arguments");
-        ZK_REQUIRE(g_msm_ev_made, "no profiled MSM has run");
+        ZK_REQUIRE(g_msm_last_profiled, "no profiled MSM has run");
+        MsmStageEvents* E = g_msm_last_profiled;
         ZK_CUDA(cudaStreamSynchronize(g_msm_ev_stream));
         for (int i = 0; i + 1 < MSM_ST_COUNT; ++i) {
             ms_out[i] = 0.f;
-            if (!g_msm_ev_valid[i]) continue;
+            if (!E->valid[i]) continue;
             int j = i + 1;
-            while (j < MSM_ST_COUNT && !g_msm_ev_valid[j]) ++j;
-            if (j < MSM_ST_COUNT) ZK_CUDA(cudaEventElapsedTime(&ms_out[i], g_msm_ev[i], g_msm_ev[j]));
+            while (j < MSM_ST_COUNT && !E->valid[j]) ++j;
+            if (j < MSM_ST_COUNT) ZK_CUDA(cudaEventElapsedTime(&ms_out[i], E->ev[i], E->ev[j]));
         }
-        info_out[0] = g_msm_info.n; info_out[1] = g_msm_info.c; info_out[2] = g_msm_info.nwin;
-        info_out[3] = g_msm_info.npairs; info_out[4] = g_msm_info.chunk;
+        if (E->d_run) {       // the plan the device made for that call (still in the stream's work arena)
+            MsmRun h;
+            ZK_CUDA(cudaMemcpy(&h, E->d_run, sizeof h, cudaMemcpyDeviceToHost));
+            E->info.npairs = h.npairs;
+            E->info.chunk = h.L;
+        }
+        info_out[0] = E->info.n; info_out[1] = E->info.c; info_out[2] = E->info.nwin;
+        info_out[3] = E->info.npairs; info_out[4] = E->info.chunk;
     });
 }
 
@@ -1121,7 +1193,7 @@ int b200zk_g1_sum(const uint64_t* points_xyz, size_t count, uint64_t out_xyz[12]
         ensure_init();
         Context& c = ctx();
         cudaStream_t s = c.stream;
-        G1Jacobian* d = (G1Jacobian*)c.misc.get((count + 1) * sizeof(G1Jacobian));
+        G1Jacobian* d = (G1Jacobian*)c.scratch(s).misc.get((count + 1) * sizeof(G1Jacobian));
         if (count) ZK_CUDA(cudaMemcpyAsync(d + 1, points_xyz, count * sizeof(G1Jacobian), cudaMemcpyHostToDevice, s));
         g1_sum_kernel<<<1, 32, 0, s>>>(d + 1, (uint32_t)count, d);
         ZK_LAUNCH_CHECK();

@@ -95,7 +95,9 @@ NttTables* ntt_get_tables(Context& c, const Fr& omega, uint32_t log_n, cudaStrea
         t->w8[0] = Fr::one();
         t->w8[1] = (log_n == 2) ? omega : Fr::one();
         t->w8[2] = Fr::one();
+        ZK_CUDA(cudaStreamSynchronize(s));
     }
+    // the tables are complete here (synchronised above), so any stream may use them from now on
     c.ntt_tables.push_back(t);
     return t;
 }
@@ -141,11 +143,11 @@ struct NttMods {
 };
 
 template <int B, bool FIRST> static void launch_pass(const NttPassArgs& a, unsigned blocks, unsigned batch, cudaStream_t s) {
-    static bool configured = false;
+    static int configured_device = -1;      // the attribute is per device (b200zk_shutdown + init may rebind)
     constexpr int smem = 2 * NTT_TILE * sizeof(uint4);
-    if (!configured) {
+    if (configured_device != ctx().device) {
         ZK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<B, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured_device = ctx().device;
     }
     ntt_pass_kernel<B, FIRST><<<dim3(blocks, batch), NTT_THREADS, smem, s>>>(a);
     ZK_LAUNCH_CHECK();
@@ -265,9 +267,19 @@ static void host_ntt(uint64_t* a, size_t stride, size_t count, uint32_t log_n, c
     check_batch(stride, count, n);
     if (count == 0) return;
     cudaStream_t s = c.stream;
-    Fr* io = (Fr*)c.ntt_io.get(count * n * sizeof(Fr));
-    Fr* tmp = (Fr*)c.ntt_tmp.get(count * n * sizeof(Fr));
-    if (count == 1 && log_n >= g_ntt_pipe_min_log_n && g_ntt_pipe_chunks > 1) {
+    // a single transform works in the buffer's device mirror when mirrors are on (b200zk_mirror_enable):
+    // no upload if an earlier call left the polynomial there, and the result stays for the next one
+    Fr* io = nullptr;
+    bool resident = false;
+    if (count == 1 && c.mirrors.enabled) {
+        io = (Fr*)c.mirrors.find(a, n);
+        resident = io != nullptr;
+        if (!io) io = (Fr*)c.mirrors.insert(a, n);
+    } else {
+        io = (Fr*)c.scratch(s).ntt_io.get(count * n * sizeof(Fr));
+    }
+    Fr* tmp = (Fr*)c.scratch(s).ntt_tmp.get(count * n * sizeof(Fr));
+    if (count == 1 && !resident && log_n >= g_ntt_pipe_min_log_n && g_ntt_pipe_chunks > 1) {
         // one large transform: upload column ranges under the first pass, download under the last
         constexpr int MAXC = NTT_PIPE_MAX_CHUNKS;
         cudaStream_t& up = g_ntt_up;
@@ -324,12 +336,27 @@ static void host_ntt(uint64_t* a, size_t stride, size_t count, uint32_t log_n, c
             return;
         }
     }
-    ZK_CUDA(cudaMemcpy2DAsync(io, n * sizeof(Fr), a, stride * sizeof(Fr), n * sizeof(Fr), count,
-                              cudaMemcpyHostToDevice, s));
+    if (!resident)
+        ZK_CUDA(cudaMemcpy2DAsync(io, n * sizeof(Fr), a, stride * sizeof(Fr), n * sizeof(Fr), count,
+                                  cudaMemcpyHostToDevice, s));
     ntt_run(c, io, n, io, n, tmp, count, log_n, omega, mods, s);
     ZK_CUDA(cudaMemcpy2DAsync(a, stride * sizeof(Fr), io, n * sizeof(Fr), n * sizeof(Fr), count,
                               cudaMemcpyDeviceToHost, s));
     ZK_CUDA(cudaStreamSynchronize(s));
+}
+
+// host Fr buffer -> device: its mirror when mirrors are on (uploaded on a miss), else `fallback` + upload
+static const Fr* host_in(Context& c, const uint64_t* host, size_t n_elems, Arena& fallback, cudaStream_t s) {
+    if (c.mirrors.enabled && n_elems) {
+        Fr* d = (Fr*)c.mirrors.find(host, n_elems);
+        if (d) return d;
+        d = (Fr*)c.mirrors.insert(host, n_elems);
+        ZK_CUDA(cudaMemcpyAsync(d, host, n_elems * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        return d;
+    }
+    Fr* d = (Fr*)fallback.get(std::max<size_t>(n_elems, 1) * sizeof(Fr));
+    ZK_CUDA(cudaMemcpyAsync(d, host, n_elems * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    return d;
 }
 
 static NttMods scale_mods(const uint64_t* divisor) {
@@ -520,11 +547,19 @@ int b200zk_coeff_to_extended_many(const uint64_t* in, size_t in_stride, uint64_t
         check_batch(out_stride, count, N);
         if (count == 0) return;
         cudaStream_t s = c.stream;
-        Fr* din = (Fr*)c.ntt_aux.get(count * n * sizeof(Fr));
-        Fr* io = (Fr*)c.ntt_io.get(count * N * sizeof(Fr));
-        Fr* tmp = (Fr*)c.ntt_tmp.get(count * N * sizeof(Fr));
-        ZK_CUDA(cudaMemcpy2DAsync(din, n * sizeof(Fr), in, in_stride * sizeof(Fr), n * sizeof(Fr), count,
-                                  cudaMemcpyHostToDevice, s));
+        Fr* tmp = (Fr*)c.scratch(s).ntt_tmp.get(count * N * sizeof(Fr));
+        const Fr* din = nullptr;
+        Fr* io = nullptr;
+        if (count == 1 && c.mirrors.enabled) {
+            din = host_in(c, in, n, c.scratch(s).ntt_aux, s);
+            io = (Fr*)c.mirrors.insert(out, N, in);          // the extended column stays in HBM for evaluate_h
+        } else {
+            Fr* up = (Fr*)c.scratch(s).ntt_aux.get(count * n * sizeof(Fr));
+            io = (Fr*)c.scratch(s).ntt_io.get(count * N * sizeof(Fr));
+            ZK_CUDA(cudaMemcpy2DAsync(up, n * sizeof(Fr), in, in_stride * sizeof(Fr), n * sizeof(Fr), count,
+                                      cudaMemcpyHostToDevice, s));
+            din = up;
+        }
         ntt_run(c, din, n, io, N, tmp, count, ext_k, fr_from_limbs(extended_omega), coset_in_mods(k, zeta), s);
         ZK_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(Fr), io, N * sizeof(Fr), N * sizeof(Fr), count,
                                   cudaMemcpyDeviceToHost, s));
@@ -543,13 +578,16 @@ int b200zk_extended_to_coeff(const uint64_t* a, uint32_t ext_k, const uint64_t e
         ensure_init();
         Context& c = ctx();
         cudaStream_t s = c.stream;
-        Fr* din = (Fr*)c.ntt_aux.get(N * sizeof(Fr));
-        Fr* io = (Fr*)c.ntt_io.get(N * sizeof(Fr));
-        Fr* tmp = (Fr*)c.ntt_tmp.get(N * sizeof(Fr));
-        ZK_CUDA(cudaMemcpyAsync(din, a, N * sizeof(Fr), cudaMemcpyHostToDevice, s));
-        NttMods m = coset_out_mods(extended_ifft_divisor, zeta, keep);
         if (keep == 0) return;
+        Fr* io = (Fr*)c.scratch(s).ntt_io.get(N * sizeof(Fr));
+        Fr* tmp = (Fr*)c.scratch(s).ntt_tmp.get(N * sizeof(Fr));
+        const Fr* din = host_in(c, a, N, c.scratch(s).ntt_aux, s);
+        NttMods m = coset_out_mods(extended_ifft_divisor, zeta, keep);
         ntt_run(c, din, N, io, N, tmp, 1, ext_k, fr_from_limbs(extended_omega_inv), m, s);
+        if (c.mirrors.enabled) {     // the pieces of h(X) are committed next (as slices of `out`): leave them in HBM
+            void* dm = c.mirrors.insert(out, keep, a);
+            ZK_CUDA(cudaMemcpyAsync(dm, io, keep * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+        }
         ZK_CUDA(cudaMemcpyAsync(out, io, keep * sizeof(Fr), cudaMemcpyDeviceToHost, s));
         ZK_CUDA(cudaStreamSynchronize(s));
     });
@@ -563,9 +601,8 @@ int b200zk_divide_by_vanishing(uint64_t* h, uint32_t ext_k, const uint64_t* t_ev
         Context& c = ctx();
         cudaStream_t s = c.stream;
         const uint64_t N = (uint64_t)1 << ext_k;
-        Fr* io = (Fr*)c.ntt_io.get(N * sizeof(Fr));
-        Fr* tab = (Fr*)c.ntt_aux.get((size_t)t_len * sizeof(Fr));
-        ZK_CUDA(cudaMemcpyAsync(io, h, N * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        Fr* io = const_cast<Fr*>(host_in(c, h, N, c.scratch(s).ntt_io, s));   // in place (in the mirror when on)
+        Fr* tab = (Fr*)c.scratch(s).ntt_aux.get((size_t)t_len * sizeof(Fr));
         ZK_CUDA(cudaMemcpyAsync(tab, t_evaluations, (size_t)t_len * sizeof(Fr), cudaMemcpyHostToDevice, s));
         fr_scale_table_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(io, N, tab, t_len - 1);
         ZK_LAUNCH_CHECK();
@@ -584,7 +621,7 @@ int b200zk_ntt_dev(void* d_a, size_t stride, size_t count, uint32_t log_n, const
         const uint64_t n = (uint64_t)1 << log_n;
         check_batch(stride, count, n);
         cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
-        Fr* tmp = (Fr*)c.ntt_tmp.get(count * n * sizeof(Fr));
+        Fr* tmp = (Fr*)c.scratch(s).ntt_tmp.get(count * n * sizeof(Fr));
         ntt_run(c, (Fr*)d_a, stride, (Fr*)d_a, stride, tmp, count, log_n, fr_from_limbs(omega),
                 scale_mods(divisor_or_null), s);
     });
@@ -603,7 +640,7 @@ int b200zk_coeff_to_extended_dev(const void* d_in, size_t in_stride, void* d_out
         check_batch(in_stride, count, n);
         check_batch(out_stride, count, N);
         cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
-        Fr* tmp = (Fr*)c.ntt_tmp.get(count * N * sizeof(Fr));
+        Fr* tmp = (Fr*)c.scratch(s).ntt_tmp.get(count * N * sizeof(Fr));
         ntt_run(c, (const Fr*)d_in, in_stride, (Fr*)d_out, out_stride, tmp, count, ext_k,
                 fr_from_limbs(extended_omega), coset_in_mods(k, zeta), s);
     });
@@ -630,8 +667,8 @@ int b200zk_extended_to_coeff_dev(const void* d_a, uint32_t ext_k, const uint64_t
             m.in_table_mask = t_len - 1;
         }
         // result needs N slots while passes run; d_out may be shorter, so work in scratch
-        Fr* io = (Fr*)c.ntt_io.get(N * sizeof(Fr));
-        Fr* tmp = (Fr*)c.ntt_tmp.get(N * sizeof(Fr));
+        Fr* io = (Fr*)c.scratch(s).ntt_io.get(N * sizeof(Fr));
+        Fr* tmp = (Fr*)c.scratch(s).ntt_tmp.get(N * sizeof(Fr));
         ntt_run(c, (const Fr*)d_a, N, io, N, tmp, 1, ext_k, fr_from_limbs(extended_omega_inv), m, s);
         ZK_CUDA(cudaMemcpyAsync(d_out, io, keep * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
     });
@@ -703,13 +740,13 @@ int b200zk_coeff_to_coset_dev(const void* d_in, size_t in_stride, void* d_out, s
         if (count == 0) return;
         cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
         // powers of the coset generator, one table per call (n entries, ~30 products each)
-        Fr* pw = (Fr*)c.ntt_aux.get(n * sizeof(Fr));
+        Fr* pw = (Fr*)c.scratch(s).ntt_aux.get(n * sizeof(Fr));
         fr_pow_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(fr_from_limbs(coset_generator), 1, (uint32_t)n, pw);
         ZK_LAUNCH_CHECK();
         fr_scale_pow_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)count), 256, 0, s>>>(
             (const Fr*)d_in, in_stride, (Fr*)d_out, out_stride, (uint32_t)n, pw);
         ZK_LAUNCH_CHECK();
-        Fr* tmp = (Fr*)c.ntt_tmp.get(count * n * sizeof(Fr));
+        Fr* tmp = (Fr*)c.scratch(s).ntt_tmp.get(count * n * sizeof(Fr));
         ntt_run(c, (Fr*)d_out, out_stride, (Fr*)d_out, out_stride, tmp, count, k, fr_from_limbs(omega), NttMods(), s);
     });
 }

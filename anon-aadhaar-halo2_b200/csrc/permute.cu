@@ -271,7 +271,7 @@ int b200zk_permute_expression_pair_dev(const void* d_input, const void* d_table,
         const size_t o_a = carve(col_bytes * count), o_t = carve(col_bytes * count), o_l = carve(col_bytes * count);
         const size_t o_rr = carve((size_t)padded * 4 * count), o_cnt = carve((size_t)count * 12);
         const size_t o_bl = carve(std::max<size_t>(1, (size_t)count * 2 * nbl) * sizeof(Fr));
-        char* w = (char*)c.poly_cols.get(off);
+        char* w = (char*)c.scratch(s).poly_cols.get(off);
         Key* A = (Key*)(w + o_a);
         Key* T = (Key*)(w + o_t);
         Key* L = (Key*)(w + o_l);
@@ -280,13 +280,13 @@ int b200zk_permute_expression_pair_dev(const void* d_input, const void* d_table,
         Fr* bl = nullptr;
         if (blinds_or_null) {
             bl = (Fr*)(w + o_bl);
-            ZK_CUDA(cudaMemcpyAsync(bl, blinds_or_null, (size_t)count * 2 * nbl * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            c.scratch(s).staging.copy(bl, blinds_or_null, (size_t)count * 2 * nbl * sizeof(Fr), s);
         }
-        static bool configured = false;
-        if (!configured) {
+        static int configured_device = -1;      // per-device attribute (see ntt.cu launch_pass)
+        if (configured_device != c.device) {
             ZK_CUDA(cudaFuncSetAttribute(sort_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(SORT_TILE * sizeof(Key))));
-            configured = true;
+            configured_device = c.device;
         }
         const dim3 lgrid((padded + 255) / 256, count);
         sort_load_kernel<<<lgrid, 256, 0, s>>>((const Fr*)d_input, stride, m, padded, A);

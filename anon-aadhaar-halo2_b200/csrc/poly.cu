@@ -186,7 +186,7 @@ static void prefix_product_run(Context& c, const Fr* in, size_t in_stride, Fr* o
                                size_t n, const Fr* first, cudaStream_t s) {
     if (count == 0 || n == 0) return;
     const uint32_t nblocks = (uint32_t)((n + PB - 1) / PB);
-    Fr* scratch = (Fr*)c.poly_scan.get((count * nblocks * (PT + 1) + 1) * sizeof(Fr));
+    Fr* scratch = (Fr*)c.scratch(s).poly_scan.get((count * nblocks * (PT + 1) + 1) * sizeof(Fr));
     Fr* thread_prefix = scratch;
     Fr* block_total = scratch + count * nblocks * PT;
     pp_block_kernel<<<dim3(nblocks, (unsigned)count), PT, 0, s>>>(in, in_stride, n, thread_prefix, block_total, nblocks);
@@ -423,7 +423,7 @@ int b200zk_batch_invert_dev(void* d_a, size_t n, void* stream) {
         ensure_init();
         Context& c = ctx();
         cudaStream_t s = pick_stream(stream);
-        Fr* scratch = (Fr*)c.poly_work.get(batch_invert_scratch_elems(n) * sizeof(Fr));
+        Fr* scratch = (Fr*)c.scratch(s).poly_work.get(batch_invert_scratch_elems(n) * sizeof(Fr));
         batch_invert_run((Fr*)d_a, n, scratch, s);
     });
 }
@@ -435,8 +435,8 @@ int b200zk_batch_invert(uint64_t* a, size_t n) {
         ensure_init();
         Context& c = ctx();
         cudaStream_t s = c.stream;
-        Fr* d = (Fr*)c.ntt_io.get(n * sizeof(Fr));
-        Fr* scratch = (Fr*)c.poly_work.get(batch_invert_scratch_elems(n) * sizeof(Fr));
+        Fr* d = (Fr*)c.scratch(s).ntt_io.get(n * sizeof(Fr));
+        Fr* scratch = (Fr*)c.scratch(s).poly_work.get(batch_invert_scratch_elems(n) * sizeof(Fr));
         ZK_CUDA(cudaMemcpyAsync(d, a, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
         batch_invert_run(d, n, scratch, s);
         ZK_CUDA(cudaMemcpyAsync(a, d, n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
@@ -455,8 +455,8 @@ int b200zk_prefix_product_dev(const void* d_in, size_t in_stride, void* d_out, s
         cudaStream_t s = pick_stream(stream);
         Fr* first = nullptr;
         if (first_or_null && count) {
-            first = (Fr*)c.poly_small.get(count * sizeof(Fr));
-            ZK_CUDA(cudaMemcpyAsync(first, first_or_null, count * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            first = (Fr*)c.scratch(s).poly_small.get(count * sizeof(Fr));
+            c.scratch(s).staging.copy(first, first_or_null, count * sizeof(Fr), s);
         }
         prefix_product_run(c, (const Fr*)d_in, in_stride, (Fr*)d_out, out_stride, count, n, first, s);
         if (first) ZK_CUDA(cudaStreamSynchronize(s));   // the host array may go away after return
@@ -489,25 +489,25 @@ int b200zk_permutation_product_dev(const void* const* d_values, const void* cons
         auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
         const size_t o_v = carve(ptr_bytes), o_s = carve(ptr_bytes), o_db = carve(n_cols * sizeof(Fr));
         const size_t o_chain = carve(n_sets * sizeof(Fr)), o_bl = carve(std::max<size_t>(n_blind_elems, 1) * sizeof(Fr));
-        char* small = (char*)c.poly_small.get(off);
+        char* small = (char*)c.scratch(s).poly_small.get(off);
         for (uint32_t j = 0; j < n_cols; ++j) ZK_REQUIRE(d_values[j] && d_sigma[j], "null column pointer");
-        ZK_CUDA(cudaMemcpyAsync(small + o_v, d_values, ptr_bytes, cudaMemcpyHostToDevice, s));
-        ZK_CUDA(cudaMemcpyAsync(small + o_s, d_sigma, ptr_bytes, cudaMemcpyHostToDevice, s));
-        ZK_CUDA(cudaMemcpyAsync(small + o_db, db.data(), n_cols * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        c.scratch(s).staging.copy(small + o_v, d_values, ptr_bytes, s);
+        c.scratch(s).staging.copy(small + o_s, d_sigma, ptr_bytes, s);
+        c.scratch(s).staging.copy(small + o_db, db.data(), n_cols * sizeof(Fr), s);
         if (n_blind_elems)
-            ZK_CUDA(cudaMemcpyAsync(small + o_bl, blinds_or_null, n_blind_elems * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            c.scratch(s).staging.copy(small + o_bl, blinds_or_null, n_blind_elems * sizeof(Fr), s);
         PermProdArgs A;
         A.values = (const Fr* const*)(small + o_v);
         A.sigma = (const Fr* const*)(small + o_s);
         A.delta_beta = (const Fr*)(small + o_db);
-        A.work = (Fr*)c.poly_cols.get((size_t)n_sets * n * sizeof(Fr));
+        A.work = (Fr*)c.scratch(s).poly_cols.get((size_t)n_sets * n * sizeof(Fr));
         A.tw_lo = t->tw_lo; A.tw_hi = t->tw_hi; A.tw_h = t->tw_h;
         A.n_cols = n_cols; A.chunk_len = chunk_len; A.log_n = k;
         A.beta = b; A.gamma = g;
         const dim3 grid((n + 255) / 256, n_sets);
         perm_denominator_kernel<<<grid, 256, 0, s>>>(A);
         ZK_LAUNCH_CHECK();
-        Fr* scratch = (Fr*)c.poly_work.get(batch_invert_scratch_elems((size_t)n_sets * n) * sizeof(Fr));
+        Fr* scratch = (Fr*)c.scratch(s).poly_work.get(batch_invert_scratch_elems((size_t)n_sets * n) * sizeof(Fr));
         batch_invert_run(A.work, (size_t)n_sets * n, scratch, s);
         perm_numerator_kernel<<<grid, 256, 0, s>>>(A);
         ZK_LAUNCH_CHECK();
@@ -542,26 +542,26 @@ int b200zk_lookup_product_dev(const void* const* d_compressed_input, const void*
         auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
         const size_t o_p[4] = {carve(ptr_bytes), carve(ptr_bytes), carve(ptr_bytes), carve(ptr_bytes)};
         const size_t o_bl = carve(std::max<size_t>(n_blind_elems, 1) * sizeof(Fr));
-        char* small = (char*)c.poly_small.get(off);
+        char* small = (char*)c.scratch(s).poly_small.get(off);
         const void* const* srcs[4] = {d_compressed_input, d_compressed_table, d_permuted_input, d_permuted_table};
         for (int a = 0; a < 4; ++a) {
             for (uint32_t j = 0; j < count; ++j) ZK_REQUIRE(srcs[a][j], "null column pointer");
-            ZK_CUDA(cudaMemcpyAsync(small + o_p[a], srcs[a], ptr_bytes, cudaMemcpyHostToDevice, s));
+            c.scratch(s).staging.copy(small + o_p[a], srcs[a], ptr_bytes, s);
         }
         if (n_blind_elems)
-            ZK_CUDA(cudaMemcpyAsync(small + o_bl, blinds_or_null, n_blind_elems * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            c.scratch(s).staging.copy(small + o_bl, blinds_or_null, n_blind_elems * sizeof(Fr), s);
         LookupProdArgs A;
         A.compressed_input = (const Fr* const*)(small + o_p[0]);
         A.compressed_table = (const Fr* const*)(small + o_p[1]);
         A.permuted_input = (const Fr* const*)(small + o_p[2]);
         A.permuted_table = (const Fr* const*)(small + o_p[3]);
-        A.work = (Fr*)c.poly_cols.get((size_t)count * n * sizeof(Fr));
+        A.work = (Fr*)c.scratch(s).poly_cols.get((size_t)count * n * sizeof(Fr));
         A.log_n = k;
         A.beta = fr_from_limbs(beta); A.gamma = fr_from_limbs(gamma);
         const dim3 grid((n + 255) / 256, count);
         lookup_denominator_kernel<<<grid, 256, 0, s>>>(A);
         ZK_LAUNCH_CHECK();
-        Fr* scratch = (Fr*)c.poly_work.get(batch_invert_scratch_elems((size_t)count * n) * sizeof(Fr));
+        Fr* scratch = (Fr*)c.scratch(s).poly_work.get(batch_invert_scratch_elems((size_t)count * n) * sizeof(Fr));
         batch_invert_run(A.work, (size_t)count * n, scratch, s);
         lookup_numerator_kernel<<<grid, 256, 0, s>>>(A);
         ZK_LAUNCH_CHECK();
@@ -594,11 +594,11 @@ int b200zk_eval_polynomial_dev(const void* d_polys, size_t stride, size_t count,
         do sizes.push_back((sizes.back() + PB - 1) / PB); while (sizes.back() > 1);
         size_t partial_elems = 0;
         for (size_t i = 1; i < sizes.size(); ++i) partial_elems += sizes[i] * count;
-        Fr* work = (Fr*)c.poly_work.get((partial_elems + 2 * count + 1) * sizeof(Fr));
+        Fr* work = (Fr*)c.scratch(s).poly_work.get((partial_elems + 2 * count + 1) * sizeof(Fr));
         Fr* pts_a = work;
         Fr* pts_b = work + count;
         Fr* partial = work + 2 * count;
-        ZK_CUDA(cudaMemcpyAsync(pts_a, points, count * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        c.scratch(s).staging.copy(pts_a, points, count * sizeof(Fr), s);
         const Fr* src = (const Fr*)d_polys;
         size_t src_stride = stride;
         uint32_t log_tile = 0;
@@ -631,11 +631,11 @@ int b200zk_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], voi
         cudaStream_t s = pick_stream(stream);
         const Fr bb = fr_from_limbs(b);
         const uint32_t ntiles = (uint32_t)((n + PB - 1) / PB);
-        Fr* work = (Fr*)c.poly_work.get((2 * (size_t)ntiles + 2) * sizeof(Fr));
+        Fr* work = (Fr*)c.scratch(s).poly_work.get((2 * (size_t)ntiles + 2) * sizeof(Fr));
         Fr* tile_sums = work;
         Fr* carry_in = work + ntiles;
         Fr* pt = work + 2 * (size_t)ntiles;
-        ZK_CUDA(cudaMemcpyAsync(pt, &bb, sizeof(Fr), cudaMemcpyHostToDevice, s));
+        c.scratch(s).staging.copy(pt, &bb, sizeof(Fr), s);
         eval_level_kernel<<<dim3(ntiles, 1), PT, 0, s>>>((const Fr*)d_a, n, n, pt, tile_sums, ntiles);
         ZK_LAUNCH_CHECK();
         kate_carry_kernel<<<1, 32, 0, s>>>(tile_sums, ntiles, bb.pow_u64((uint64_t)PB), carry_in);
@@ -657,11 +657,11 @@ int b200zk_linear_combination_dev(const void* const* d_polys, const uint64_t* co
         cudaStream_t s = pick_stream(stream);
         const size_t ptr_bytes = (size_t)count * sizeof(void*);
         const size_t o_c = (ptr_bytes + 255) / 256 * 256;
-        char* small = (char*)c.poly_small.get(o_c + (size_t)count * sizeof(Fr) + 256);
+        char* small = (char*)c.scratch(s).poly_small.get(o_c + (size_t)count * sizeof(Fr) + 256);
         for (uint32_t j = 0; j < count; ++j) ZK_REQUIRE(d_polys[j], "null column pointer");
         if (count) {
-            ZK_CUDA(cudaMemcpyAsync(small, d_polys, ptr_bytes, cudaMemcpyHostToDevice, s));
-            ZK_CUDA(cudaMemcpyAsync(small + o_c, coeffs, (size_t)count * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            c.scratch(s).staging.copy(small, d_polys, ptr_bytes, s);
+            c.scratch(s).staging.copy(small + o_c, coeffs, (size_t)count * sizeof(Fr), s);
         }
         linear_combination_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const Fr* const*)small, (const Fr*)(small + o_c),
                                                                              count, n, (Fr*)d_out);

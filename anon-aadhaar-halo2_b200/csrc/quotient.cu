@@ -222,10 +222,16 @@ struct PtrStager {
         for (uint32_t i = 0; i < n; ++i) host.push_back(col_ptr(c, handles[i], size, what));
         return off;
     }
+    // staged through a library-owned page-locked slot (the handle list is the caller's memory)
     const Fr* const* upload(Context& c, cudaStream_t s) {
-        const Fr** d = (const Fr**)c.quot_ptrs.get((host.size() + 1) * sizeof(const Fr*));
-        if (!host.empty())
-            ZK_CUDA(cudaMemcpyAsync(d, host.data(), host.size() * sizeof(const Fr*), cudaMemcpyHostToDevice, s));
+        Scratch& w = c.scratch(s);
+        const Fr** d = (const Fr**)w.quot_ptrs.get((host.size() + 1) * sizeof(const Fr*));
+        if (!host.empty()) {
+            void* pin = w.staging.begin(host.size() * sizeof(const Fr*));
+            memcpy(pin, host.data(), host.size() * sizeof(const Fr*));
+            ZK_CUDA(cudaMemcpyAsync(d, pin, host.size() * sizeof(const Fr*), cudaMemcpyHostToDevice, s));
+            w.staging.done(s);
+        }
         return d;
     }
 };
@@ -303,7 +309,11 @@ int b200zk_dev_upload(uint64_t handle, size_t offset, const uint64_t* host, size
         Context& c = ctx();
         DevBuffer& b = buffer_of(c, handle, offset + n_elems, "upload");
         ZK_REQUIRE(host || n_elems == 0, "null argument");
-        ZK_CUDA(cudaMemcpyAsync((Fr*)b.p + offset, host, n_elems * sizeof(Fr), cudaMemcpyHostToDevice, c.stream));
+        const void* mirror = n_elems ? c.mirrors.find(host, n_elems) : nullptr;    // null when mirrors are off
+        if (mirror)
+            ZK_CUDA(cudaMemcpyAsync((Fr*)b.p + offset, mirror, n_elems * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
+        else
+            ZK_CUDA(cudaMemcpyAsync((Fr*)b.p + offset, host, n_elems * sizeof(Fr), cudaMemcpyHostToDevice, c.stream));
         ZK_CUDA(cudaStreamSynchronize(c.stream));
     });
 }
@@ -314,6 +324,10 @@ int b200zk_dev_download(uint64_t handle, size_t offset, uint64_t* host, size_t n
         Context& c = ctx();
         DevBuffer& b = buffer_of(c, handle, offset + n_elems, "download");
         ZK_REQUIRE(host || n_elems == 0, "null argument");
+        if (c.mirrors.enabled && n_elems) {      // the host buffer now equals this device range: keep a mirror
+            void* dm = c.mirrors.insert(host, n_elems);
+            ZK_CUDA(cudaMemcpyAsync(dm, (Fr*)b.p + offset, n_elems * sizeof(Fr), cudaMemcpyDeviceToDevice, c.stream));
+        }
         ZK_CUDA(cudaMemcpyAsync(host, (Fr*)b.p + offset, n_elems * sizeof(Fr), cudaMemcpyDeviceToHost, c.stream));
         ZK_CUDA(cudaStreamSynchronize(c.stream));
     });
@@ -369,15 +383,21 @@ int b200zk_quotient_graph(const b200zk_graph* g, const b200zk_quotient_env* env,
         const size_t o_calc = carve((size_t)g->n_calcs * sizeof(b200zk_calc));
         const size_t o_parts = carve((size_t)g->n_parts * sizeof(b200zk_src));
         const size_t o_chal = carve((size_t)env->n_challenges * sizeof(Fr));
-        char* base = (char*)c.quot_graph.get(off + 256);
+        Scratch& w = c.scratch(s);
+        char* base = (char*)w.quot_graph.get(off + 256);
+        // one page-locked image of the graph, one copy: the caller's arrays (which it may have page-locked
+        // itself) are read before the call returns, not by a DMA that is still queued
+        char* pin = (char*)w.staging.begin(off + 256);
         auto up = [&](size_t o, const void* src, size_t bytes) {
-            if (bytes) ZK_CUDA(cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s));
+            if (bytes) memcpy(pin + o, src, bytes);
         };
         up(o_const, g->constants, (size_t)g->n_constants * sizeof(Fr));
         up(o_rot, g->rotations, (size_t)g->n_rotations * 4);
         up(o_calc, g->calcs, (size_t)g->n_calcs * sizeof(b200zk_calc));
         up(o_parts, g->parts, (size_t)g->n_parts * sizeof(b200zk_src));
         up(o_chal, env->challenges, (size_t)env->n_challenges * sizeof(Fr));
+        if (off) ZK_CUDA(cudaMemcpyAsync(base, pin, off, cudaMemcpyHostToDevice, s));
+        w.staging.done(s);
         PtrStager ps;
         const size_t pf = ps.add(c, env->fixed, env->n_fixed, size, "fixed column");
         const size_t pa = ps.add(c, env->advice, env->n_advice, size, "advice column");
@@ -408,9 +428,9 @@ int b200zk_quotient_graph(const b200zk_graph* g, const b200zk_quotient_env* env,
         else if (g->n_intermediates <= 256) quotient_graph_kernel<256><<<blocks, 128, 0, s>>>(G);
         else quotient_graph_kernel<1024><<<blocks, 128, 0, s>>>(G);
         ZK_LAUNCH_CHECK();
-        // no synchronisation: inputs were staged from pageable memory (copied before the call
-        // returns), outputs stay on the device, and the next call is ordered behind this one on the
-        // library stream (24 lookups = 48 launches per proof: a sync each would cost more than the kernels)
+        // no synchronisation: inputs were staged through library-owned page-locked slots (copied before
+        // the call returns), outputs stay on the device, and the next call is ordered behind this one on
+        // the library stream (24 lookups = 48 launches per proof: a sync each would cost more than the kernels)
     });
 }
 

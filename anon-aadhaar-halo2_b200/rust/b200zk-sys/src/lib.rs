@@ -38,6 +38,10 @@ extern "C" {
     pub fn b200zk_shutdown() -> c_int;
     pub fn b200zk_last_error() -> *const c_char;
     pub fn b200zk_abi_version() -> u32;
+    pub fn b200zk_stream_release(stream: *mut c_void) -> c_int;
+    pub fn b200zk_mirror_enable(max_bytes: usize) -> c_int;
+    pub fn b200zk_mirror_invalidate(host_ptr: *const c_void, bytes: usize) -> c_int;
+    pub fn b200zk_mirror_stats(out: *mut u64) -> c_int;
 
     pub fn b200zk_ntt(a: *mut u64, log_n: u32, omega: *const u64) -> c_int;
     pub fn b200zk_intt(a: *mut u64, log_n: u32, omega_inv: *const u64, divisor: *const u64) -> c_int;

@@ -17,8 +17,13 @@
  *   - Every function returns 0 on success, non-zero on failure; the message is
  *     available from b200zk_last_error().  Upstream's functions are infallible and
  *     assert on bad lengths, so the Rust shim panics with that message.
- *   - Host pointers are never retained past the call.  `*_dev` entry points take device
- *     pointers and a CUDA stream and are asynchronous on that stream.
+ *   - Host pointers are never retained past the call (small host tables a `*_dev` call reads are
+ *     copied into library-owned page-locked slots before it returns).  `*_dev` entry points take
+ *     device pointers and a CUDA stream and are asynchronous on that stream: they return without
+ *     waiting for the device.  Calls are serialised on the host by one mutex, but the work they
+ *     queue on different streams runs concurrently: every stream the library is called on gets its
+ *     own scratch space (b200zk_stream_release frees it), so two MSMs / transforms on two streams
+ *     do not share any work buffer.  Ordering between streams is the caller's (events).
  *   - No CPU fallback exists: without a CUDA device every compute call fails.
  */
 #ifndef B200ZK_H
@@ -38,6 +43,9 @@ int b200zk_shutdown(void);
 const char* b200zk_last_error(void);
 /* ABI version of this header (checked by the bindings). */
 uint32_t b200zk_abi_version(void);
+/* Free the scratch space the library keeps for `stream` (NULL = its own stream); call it before
+ * destroying a stream that was passed to `*_dev` entry points.  Synchronises the device. */
+int b200zk_stream_release(void* stream);
 
 /* ---- host memory ------------------------------------------------------------------- */
 /* Every host-pointer entry point accepts pageable memory (a Rust `Vec<Fr>`), but the driver then
@@ -51,6 +59,25 @@ int b200zk_host_register(void* ptr, size_t bytes);
 int b200zk_host_unregister(void* ptr);
 int b200zk_host_alloc(size_t bytes, void** ptr_out);
 int b200zk_host_free(void* ptr);
+
+/* Device mirrors of host polynomials (off by default).  `create_proof` hands the same `Polynomial`
+ * to several of the calls below in a row — commit_lagrange(p), lagrange_to_coeff(p),
+ * coeff_to_extended(&p), evaluate_h(.., p, ..) — and every call would upload it again.  With
+ * b200zk_mirror_enable(max_bytes > 0) each host Fr buffer a host-pointer call reads is kept in HBM,
+ * keyed by (pointer, length), and a call that writes a host buffer (the in-place transforms, the
+ * `out` of coeff_to_extended / extended_to_coeff, b200zk_dev_download) leaves its mirror equal to
+ * what it wrote; later calls on the same buffer skip the upload (b200zk_dev_upload copies device to
+ * device).  Results are the same bytes either way.  The contract that makes this sound: while mirrors
+ * are on, the caller calls b200zk_mirror_invalidate(ptr, bytes) before it writes or frees host memory
+ * it has passed to a host-pointer call (bytes = 0: whatever mirror contains `ptr`).  The Rust fork
+ * keeps that contract inside `Polynomial` (a `Cell<bool>` set when the buffer is handed to the
+ * library, checked in `DerefMut` and `Drop`) and invalidates immediately after a call on a plain
+ * slice (`best_multiexp`, `best_fft`), see INTEGRATION.md.  Least-recently-used mirrors are dropped
+ * beyond max_bytes; max_bytes = 0 drops everything and turns mirroring off.
+ * b200zk_mirror_stats: {hits, misses, resident bytes, evictions}. */
+int b200zk_mirror_enable(size_t max_bytes);
+int b200zk_mirror_invalidate(const void* host_ptr, size_t bytes);
+int b200zk_mirror_stats(uint64_t out[4]);
 
 /* ---- NTT: arithmetic::best_fft and EvaluationDomain -------------------------------- */
 /* halo2_proofs/src/arithmetic.rs `best_fft::<Fr>(a, omega, log_n)`: in place,
@@ -147,7 +174,8 @@ int b200zk_bases_register(const uint64_t* bases, size_t n, uint64_t* handle_out)
 /* Same with control over the per-window table T[w][i] = 2^(c*w) * bases[i] that registration
  * builds by default (W x the memory of the bases; every window then shares one bucket set and
  * the final doubling chain disappears — the win for the prover's 2^15..2^17 commitments).
- * precompute_windows = 0 keeps only the points. */
+ * precompute_windows = 0 keeps only the points, 1 lets the cost model choose the window size,
+ * 4..23 forces that many window bits. */
 int b200zk_bases_register_ex(const uint64_t* bases, size_t n, int precompute_windows, uint64_t* handle_out);
 int b200zk_bases_evict(uint64_t handle);
 int b200zk_msm_g1_registered(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]);
@@ -156,8 +184,8 @@ int b200zk_msm_g1_registered(uint64_t handle, const uint64_t* scalars, size_t n,
  * entry point behind create_proof's `advice.iter().map(|p| params.commit_lagrange(p))`. */
 int b200zk_msm_g1_registered_many(uint64_t handle, const uint64_t* scalars, size_t stride, size_t count, size_t n,
                                   uint64_t* out_xyz);
-/* Device-resident scalars and results (count x 12 limbs at d_out_xyz), asynchronous on `stream`
- * apart from one internal synchronisation. */
+/* Device-resident scalars and results (count x 12 limbs at d_out_xyz), asynchronous on `stream`:
+ * the pair count the sort produces stays on the device (it plans the accumulation there). */
 int b200zk_msm_g1_registered_dev(uint64_t handle, const void* d_scalars, size_t stride, size_t count, size_t n,
                                  void* d_out_xyz, void* stream);
 

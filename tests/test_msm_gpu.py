@@ -7,7 +7,7 @@ import pytest
 
 from oracle import bn254 as bn
 from oracle import c_oracle as co
-from util import GOLDEN, jac_affine
+from util import GOLDEN, fr1, jac_affine, omega_for
 
 pytestmark = pytest.mark.gpu
 
@@ -225,3 +225,73 @@ def test_commit_upload_pipeline_same_point(zk, parts, n):
     assert one_shot == want
     assert piped == want
     assert piped_short == jac_affine(co.best_multiexp(s[: n - 3], g[: n - 3]))
+
+
+def test_two_commits_on_two_streams_run_concurrently_and_agree(zk):
+    """`*_dev` calls are asynchronous and stream-safe: two different commitments queued back to back on
+    two streams (no host synchronisation in between, so their kernels overlap on the device and would
+    trample a shared scratch arena) give the points the same calls give one at a time; the same for a
+    commit on one stream under a transform on another."""
+    import torch
+
+    lib = zk.load()
+    k = 16
+    n = 1 << k
+    pts = co.gen_points(0xBA5E0000 + k, n)
+    h = C.c_uint64(0)
+    zk.check(lib.b200zk_bases_register(C.c_void_p(pts.ctypes.data), n, C.byref(h)))
+    sa = torch.from_numpy(co.gen_scalars(1, n).view(np.int64).reshape(-1)).cuda()
+    sb = torch.from_numpy(co.gen_scalars(2, n).view(np.int64).reshape(-1)).cuda()
+    db = torch.from_numpy(pts.view(np.int64).reshape(-1)).cuda()
+    ref = torch.zeros(4, 12, dtype=torch.int64, device="cuda")
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    zk.check(lib.b200zk_msm_g1_registered_dev(h.value, vp(sa), n, 1, n, vp(ref[0]), None))
+    zk.check(lib.b200zk_msm_g1_registered_dev(h.value, vp(sb), n, 1, n, vp(ref[1]), None))
+    zk.check(lib.b200zk_msm_g1_dev_async(vp(sa), vp(db), n, vp(ref[2]), None))
+    zk.check(lib.b200zk_msm_g1_dev_async(vp(sb), vp(db), n, vp(ref[3]), None))
+    torch.cuda.synchronize()
+    w = fr1(omega_for(k))
+    ntt_ref = sa.clone()
+    zk.check(lib.b200zk_ntt_dev(vp(ntt_ref), n, 1, k, C.c_void_p(w.ctypes.data), None, None))
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    p1, p2 = C.c_void_p(s1.cuda_stream), C.c_void_p(s2.cuda_stream)
+    for rep in range(4):
+        got = torch.zeros(4, 12, dtype=torch.int64, device="cuda")
+        t1, t2 = sa.clone(), sb.clone()
+        torch.cuda.synchronize()
+        zk.check(lib.b200zk_msm_g1_registered_dev(h.value, vp(sa), n, 1, n, vp(got[0]), p1))
+        zk.check(lib.b200zk_msm_g1_registered_dev(h.value, vp(sb), n, 1, n, vp(got[1]), p2))
+        zk.check(lib.b200zk_msm_g1_dev_async(vp(sa), vp(db), n, vp(got[2]), p1))
+        zk.check(lib.b200zk_msm_g1_dev_async(vp(sb), vp(db), n, vp(got[3]), p2))
+        zk.check(lib.b200zk_ntt_dev(vp(t1), n, 1, k, C.c_void_p(w.ctypes.data), None, p1))
+        zk.check(lib.b200zk_msm_g1_registered_dev(h.value, vp(sa), n, 1, n, vp(got[0]), p2))
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref), rep
+        assert torch.equal(t1, ntt_ref), rep
+    exp = jac_affine(co.best_multiexp(co.gen_scalars(1, n), pts))
+    assert jac_affine(ref[0].cpu().numpy().view(np.uint64)) == exp and jac_affine(ref[2].cpu().numpy().view(np.uint64)) == exp
+    zk.check(lib.b200zk_stream_release(p1))
+    zk.check(lib.b200zk_stream_release(p2))
+    zk.check(lib.b200zk_bases_evict(h.value))
+
+
+@pytest.mark.parametrize("kind", ["zeros", "one_nonzero", "bits"])
+def test_sparse_scalars_plan_on_the_device(zk, kind):
+    """The pair count never visits the host: the accumulation is launched for the worst case and plans
+    itself from the count the sort produced.  Scalars with (almost) no non-zero digits are the far end."""
+    k = 12
+    n = 1 << k
+    pts = co.gen_points(0xBA5E0000 + k, n)
+    sc = np.zeros((n, 4), dtype=np.uint64)
+    if kind == "one_nonzero":
+        sc[n // 3] = bn.fr_array_from_canonical([bn.R - 5])[0]
+    elif kind == "bits":
+        sc[::2] = bn.fr_array_from_canonical([1])[0]
+    exp = jac_affine(co.best_multiexp(sc, pts))
+    assert jac_affine(zk.best_multiexp(sc, pts)) == exp
+    params = zk.ParamsKZG(pts, pts)
+    try:
+        assert jac_affine(params.commit_lagrange(sc)) == exp
+    finally:
+        params.close()
