@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -177,21 +178,26 @@ struct MirrorCache {
     std::map<const void*, Entry> entries;                 // keyed by host pointer
     std::multimap<size_t, void*> free_blocks;             // device blocks kept for reuse, by size in bytes
 
+    std::vector<void*> slabs;                             // device blocks come from 64 MB slabs per size class
     void* take_block(size_t bytes) {
+        if (!bytes) bytes = 32;
         auto it = free_blocks.find(bytes);
         if (it != free_blocks.end()) {
             void* p = it->second;
             free_blocks.erase(it);
             return p;
         }
-        void* p = nullptr;
-        ZK_CUDA(cudaMalloc(&p, bytes ? bytes : 32));
-        return p;
+        const size_t per = std::max<size_t>(1, ((size_t)64 << 20) / bytes);
+        void* slab = nullptr;
+        ZK_CUDA(cudaMalloc(&slab, per * bytes));
+        slabs.push_back(slab);
+        for (size_t i = 1; i < per; ++i) free_blocks.emplace(bytes, (char*)slab + i * bytes);
+        return slab;
     }
     void drop(std::map<const void*, Entry>::iterator it) {
-        const size_t bytes = it->second.n_elems * 32;
+        const size_t bytes = it->second.n_elems ? it->second.n_elems * 32 : 32;
         free_blocks.emplace(bytes, it->second.dev);        // stream-ordered reuse on the library stream
-        resident_bytes -= bytes;
+        resident_bytes -= it->second.n_elems * 32;
         entries.erase(it);
     }
     // the device copy of host range [host, host + n_elems), or null: an exact mirror, or a slice of a
@@ -243,8 +249,8 @@ struct MirrorCache {
         }
     }
     void release() {
-        for (auto& kv : entries) cudaFree(kv.second.dev);
-        for (auto& kv : free_blocks) cudaFree(kv.second);
+        for (void* p : slabs) cudaFree(p);
+        slabs.clear();
         entries.clear();
         free_blocks.clear();
         resident_bytes = 0;

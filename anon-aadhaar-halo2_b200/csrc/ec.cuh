@@ -162,4 +162,88 @@ struct alignas(16) G1Xyzz {
     }
 };
 
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------ 4-lane cooperative arithmetic
+// The latency-bound tails of the MSM (keyed reduction of a few thousand partial sums, running sums
+// over the buckets, the doubling chains of `lo * run`) are chains of dependent point operations; one
+// XYZZ addition is 14 field multiplications back to back on one lane (about 8 us on a lone warp).
+// A *quad* — four consecutive lanes of a warp holding the same operands — runs the same addition as
+// four stages of four independent multiplications, one per lane, with the products exchanged by
+// shuffles after every stage: 4 multiplications deep instead of 14.  Every lane of the warp must
+// execute these functions together (full-mask shuffles): exceptional operands are handled by
+// selecting among results, never by branching around the shuffles.
+__device__ __forceinline__ Fq quad_get(const Fq& v, int src_role) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src_role, 4);
+    return r;
+}
+__device__ __forceinline__ Fq fq_sel(bool c, const Fq& a, const Fq& b) {   // c ? a : b
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+__device__ __forceinline__ Fq fq_sel4(uint32_t role, const Fq& a, const Fq& b, const Fq& c, const Fq& d) {
+    return fq_sel(role < 2, fq_sel(role == 0, a, b), fq_sel(role == 2, c, d));
+}
+__device__ __forceinline__ G1Xyzz xyzz_sel(bool c, const G1Xyzz& a, const G1Xyzz& b) {
+    G1Xyzz r;
+    r.x = fq_sel(c, a.x, b.x); r.y = fq_sel(c, a.y, b.y); r.zz = fq_sel(c, a.zz, b.zz); r.zzz = fq_sel(c, a.zzz, b.zzz);
+    return r;
+}
+
+// 2 * a for a quad-replicated a (dbl-2008-s-1, three multiplications deep); identity stays identity.
+__device__ __forceinline__ G1Xyzz quad_dbl(const G1Xyzz& a, uint32_t role) {
+    const Fq u = a.y.dbl();
+    // stage 1: v = u^2 | x2 = x^2
+    Fq m1 = fq_sel(role == 0, u, a.x).sqr();
+    const Fq v = quad_get(m1, 0), x2 = quad_get(m1, 1);
+    const Fq m = x2.dbl() + x2;
+    // stage 2: w = u v | s = x v | mm = m^2 | zz3 = v zz
+    Fq m2 = fq_sel4(role, u, a.x, m, v) * fq_sel4(role, v, v, m, a.zz);
+    const Fq w = quad_get(m2, 0), sv = quad_get(m2, 1), mm = quad_get(m2, 2), zz3 = quad_get(m2, 3);
+    const Fq x3 = mm - sv.dbl();
+    // stage 3: m (s - x3) | w y | zzz3 = w zzz
+    Fq m3 = fq_sel4(role, m, w, w, w) * fq_sel4(role, sv - x3, a.y, a.zzz, a.zzz);
+    const Fq t0 = quad_get(m3, 0), t1 = quad_get(m3, 1), zzz3 = quad_get(m3, 2);
+    G1Xyzz r;
+    r.x = x3; r.y = t0 - t1; r.zz = zz3; r.zzz = zzz3;
+    return xyzz_sel(a.is_identity(), a, r);
+}
+
+// a + b for quad-replicated operands (add-2008-s, four multiplications deep), all exceptional cases
+// exact: identity operands, a = b (doubling) and a = -b (identity).
+__device__ __forceinline__ G1Xyzz quad_add(const G1Xyzz& a, const G1Xyzz& b, uint32_t role) {
+    // stage 1: u1 = x1 zz2 | u2 = x2 zz1 | s1 = y1 zzz2 | s2 = y2 zzz1
+    Fq m1 = fq_sel4(role, a.x, b.x, a.y, b.y) * fq_sel4(role, b.zz, a.zz, b.zzz, a.zzz);
+    const Fq u1 = quad_get(m1, 0), u2 = quad_get(m1, 1), s1 = quad_get(m1, 2), s2 = quad_get(m1, 3);
+    const Fq P = u2 - u1, R = s2 - s1;
+    // stage 2: pp = P^2 | zz12 = zz1 zz2 | rr = R^2 | zzz12 = zzz1 zzz2
+    Fq m2 = fq_sel4(role, P, a.zz, R, a.zzz) * fq_sel4(role, P, b.zz, R, b.zzz);
+    const Fq pp = quad_get(m2, 0), zz12 = quad_get(m2, 1), rr = quad_get(m2, 2), zzz12 = quad_get(m2, 3);
+    // stage 3: ppp = P pp | q = u1 pp | zz3 = zz12 pp
+    Fq m3 = fq_sel4(role, P, u1, zz12, zz12) * pp;
+    const Fq ppp = quad_get(m3, 0), q = quad_get(m3, 1), zz3 = quad_get(m3, 2);
+    const Fq x3 = rr - ppp - q.dbl();
+    // stage 4: R (q - x3) | s1 ppp | zzz3 = zzz12 ppp
+    Fq m4 = fq_sel4(role, R, s1, zzz12, zzz12) * fq_sel4(role, q - x3, ppp, ppp, ppp);
+    const Fq t0 = quad_get(m4, 0), t1 = quad_get(m4, 1), zzz3 = quad_get(m4, 2);
+    G1Xyzz r;
+    r.x = x3; r.y = t0 - t1; r.zz = zz3; r.zzz = zzz3;
+    const bool a_id = a.is_identity(), b_id = b.is_identity();
+    const bool same_x = P.is_zero(), same_y = R.is_zero();
+    // a = b: the generic formula degenerates; the doubling runs for the whole warp only when some quad needs it
+    const bool need_dbl = !a_id && !b_id && same_x && same_y;
+    if (__any_sync(0xffffffffu, need_dbl)) {
+        const G1Xyzz d = quad_dbl(a, role);
+        r = xyzz_sel(need_dbl, d, r);
+    }
+    r = xyzz_sel(!a_id && !b_id && same_x && !same_y, G1Xyzz::identity(), r);
+    r = xyzz_sel(b_id, a, r);
+    r = xyzz_sel(a_id && !b_id, b, r);
+    return r;
+}
+#endif  // __CUDACC__
+
 }  // namespace zk

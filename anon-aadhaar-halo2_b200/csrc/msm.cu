@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint32_t* bsum,
 constexpr int MSM_MAX_LEVELS = 12;
 struct MsmRun {
     uint32_t npairs, L, nthreads, pad;
-    uint32_t level_count[MSM_MAX_LEVELS];   // entries entering combine level l
+    uint32_t level_count[MSM_MAX_LEVELS];   // entries entering combine level l (bucket accumulation)
+    uint32_t level_count2[MSM_MAX_LEVELS];  // the same for the keyed reduction of the bucket-segment partials
 };
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __restrict__ out, uint32_t* __restrict__ copy,
@@ -385,13 +386,13 @@ __global__ void __launch_bounds__(128, 5) msm_accum_kernel(const G1Affine* __res
 //
 // Sequential form (throughput regime): thread t owns entries [t*L, (t+1)*L).
 __global__ void __launch_bounds__(128) msm_combine_kernel(const uint32_t* __restrict__ keys, const G1Xyzz* __restrict__ pts,
-                                                          MsmRun* __restrict__ run, uint32_t level, uint32_t L,
+                                                          uint32_t* __restrict__ counts, uint32_t level, uint32_t L,
                                                           G1Xyzz* __restrict__ buckets,
                                                           uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t count = run->level_count[level];
+    const uint32_t count = counts[level];
     const uint32_t nthreads = (count + L - 1) / L;
-    if (t == 0) run->level_count[level + 1] = nthreads;
+    if (t == 0) counts[level + 1] = nthreads;
     if (t >= nthreads) return;
     const uint32_t begin = t * L;
     const uint32_t end = min(begin + L, count);
@@ -439,13 +440,13 @@ __device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& v, uint32_t d) {
 // steps; each warp hands up one entry, so a level shrinks the list 32x for the latency of
 // five point additions.  When count <= 32 the single warp closes everything.
 __global__ void __launch_bounds__(128) msm_combine_warp_kernel(const uint32_t* __restrict__ keys,
-                                                               const G1Xyzz* __restrict__ pts, MsmRun* __restrict__ run,
+                                                               const G1Xyzz* __restrict__ pts, uint32_t* __restrict__ counts,
                                                                uint32_t level, G1Xyzz* __restrict__ buckets,
                                                                uint32_t* __restrict__ carry_key,
                                                                G1Xyzz* __restrict__ carry_pt) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t count = run->level_count[level];
-    if (gid == 0) run->level_count[level + 1] = (count + 31) / 32;
+    const uint32_t count = counts[level];
+    if (gid == 0) counts[level + 1] = (count + 31) / 32;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = gid >> 5;
     const uint32_t base = warp << 5;
@@ -482,6 +483,50 @@ __global__ void __launch_bounds__(128) msm_combine_warp_kernel(const uint32_t* _
     }
 }
 
+// Quad form (latency regime, see ec.cuh): one entry per quad, eight per warp; three segmented shuffle
+// steps of 4-deep cooperative additions close every run that ends inside the warp.  A level shrinks
+// the list 8x for the latency of ~4 short additions; a few thousand entries are gone in four levels.
+__global__ void __launch_bounds__(128) msm_combine_quad_kernel(const uint32_t* __restrict__ keys,
+                                                               const G1Xyzz* __restrict__ pts, uint32_t* __restrict__ counts,
+                                                               uint32_t level, G1Xyzz* __restrict__ buckets,
+                                                               uint32_t* __restrict__ carry_key,
+                                                               G1Xyzz* __restrict__ carry_pt) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t role = threadIdx.x & 3u, qlane = (threadIdx.x & 31u) >> 2;
+    const uint32_t count = counts[level];
+    if (gid == 0) counts[level + 1] = (count + 7) / 8;
+    const uint32_t warp = gid >> 5;
+    const uint32_t base = warp << 3;
+    if (base >= count) return;                       // whole warp beyond the list
+    const uint32_t e = base + qlane;
+    const bool valid = e < count;
+    const uint32_t key = valid ? keys[e] : MSM_PAD_KEY;
+    G1Xyzz v = valid ? ld_xyzz(pts + e) : G1Xyzz::identity();
+#pragma unroll 1
+    for (uint32_t d = 1; d < 8; d <<= 1) {
+        const uint32_t ok = __shfl_down_sync(0xffffffffu, key, 4 * d);
+        const G1Xyzz o = shfl_down_xyzz(v, 4 * d);
+        const bool take = (qlane + d < 8) && ok == key;
+        v = quad_add(v, xyzz_sel(take, o, G1Xyzz::identity()), role);
+    }
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 4);
+    const bool head = valid && ((qlane == 0) || (prev != key));
+    const uint32_t last_q = min(7u, count - base - 1u);
+    const uint32_t k_last = __shfl_sync(0xffffffffu, key, last_q * 4);
+    const bool reaches_end = (key == k_last);
+    const bool open = head && reaches_end && (base + 8 < count) && (keys[base + 8] == key);
+    const bool flush = head && !open && !v.is_identity();
+    if (__any_sync(0xffffffffu, flush)) {
+        G1Xyzz b = flush ? ld_xyzz(buckets + key) : G1Xyzz::identity();
+        b = quad_add(b, xyzz_sel(flush, v, G1Xyzz::identity()), role);
+        if (flush && role == 0) st_xyzz(buckets + key, b);
+    }
+    if (head && reaches_end && role == 0) {
+        carry_key[warp] = key;
+        st_xyzz(carry_pt + warp, open ? v : G1Xyzz::identity());
+    }
+}
+
 // --------------------------------------------------------------- 5. window reduction
 // Thread (w, seg) walks `seglen` buckets of window w from the top: run += B_b,
 // sum += run, then emits  sum + (lo-1) * run  with key w, where lo is the weight of the
@@ -514,6 +559,51 @@ __global__ void __launch_bounds__(128, 3) msm_reduce_kernel(const G1Xyzz* __rest
     }
     out_key[t] = w;
     st_xyzz(out_pt + t, sum);
+}
+
+
+// The same reduction with one *quad* per segment (ec.cuh): every running-sum step and every step of the
+// lo * run doubling chain is 3-4 multiplications deep instead of 9-14, and four times as many warps
+// share the work, which is what this latency-bound stage lacks.  All quads of a warp run the same
+// number of steps; buckets beyond the end read as the identity.
+__global__ void __launch_bounds__(128) msm_reduce_quad_kernel(const G1Xyzz* __restrict__ buckets, uint32_t nb, uint32_t seglen,
+                                                              uint32_t segs_per_win, uint32_t nwin, uint32_t lo_bits,
+                                                              uint32_t* __restrict__ counts,
+                                                              uint32_t* __restrict__ out_key, G1Xyzz* __restrict__ out_pt) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t role = threadIdx.x & 3u;
+    const uint32_t total = segs_per_win * nwin;
+    if (gid == 0) counts[0] = total;
+    const uint32_t q = gid >> 2;
+    const bool live = q < total;
+    const uint32_t t = live ? q : total - 1;
+    const uint32_t w = t / segs_per_win, seg = t % segs_per_win;
+    const uint32_t lo_idx = seg * seglen;                 // bucket index (weight = index + 1)
+    const G1Xyzz* B = buckets + (size_t)w * nb;
+    G1Xyzz run = G1Xyzz::identity(), sum = G1Xyzz::identity();
+#pragma unroll 1
+    for (uint32_t i = seglen; i > 0; --i) {
+        const uint32_t idx = lo_idx + i - 1;
+        G1Xyzz x = (idx < nb) ? ld_xyzz(B + idx) : G1Xyzz::identity();
+        run = quad_add(run, x, role);
+        sum = quad_add(sum, run, role);
+    }
+    // sum = sum_{b} (b - lo_idx) * B_b  with weights 1..seglen; add lo_idx * run
+    G1Xyzz acc = G1Xyzz::identity();
+#pragma unroll 1
+    for (int bit = (int)lo_bits - 1; bit >= 0; --bit) {
+        if (__any_sync(0xffffffffu, !acc.is_identity())) acc = quad_dbl(acc, role);
+        const bool set = ((lo_idx >> bit) & 1u) != 0;
+        if (__any_sync(0xffffffffu, set)) {
+            const G1Xyzz tsum = quad_add(acc, run, role);
+            acc = xyzz_sel(set, tsum, acc);
+        }
+    }
+    sum = quad_add(sum, acc, role);
+    if (live && role == 0) {
+        out_key[q] = w;
+        st_xyzz(out_pt + q, sum);
+    }
 }
 
 // ----------------------------------------------------------------------- 6. fold
@@ -713,22 +803,32 @@ struct MsmPre {
 // Launch the keyed-reduction levels on (keys, pts)[count] until everything has been
 // added into `buckets`.  Small inputs use short chunks: the cost of a level is the latency
 // of L dependent point additions, not throughput.
+static bool g_msm_quad = getenv("B200ZK_MSM_QUAD") ? atoi(getenv("B200ZK_MSM_QUAD")) != 0 : true;
+static uint32_t g_msm_quad_max = getenv("B200ZK_MSM_QUAD_MAX") ? (uint32_t)atoi(getenv("B200ZK_MSM_QUAD_MAX")) : (1u << 17);
+
 static void run_combine_levels(Context& c, uint32_t* keysA, G1Xyzz* ptsA, uint32_t* keysB, G1Xyzz* ptsB,
-                               uint32_t count, MsmRun* run, G1Xyzz* buckets, cudaStream_t s) {
-    // `count` bounds the entries of level 0; the exact counts are in run->level_count (device)
+                               uint32_t count, uint32_t* counts, G1Xyzz* buckets, cudaStream_t s) {
+    // `count` bounds the entries of level 0; the exact counts are in counts[level] (device)
     uint32_t level = 0;
     while (count > 0) {
         ZK_REQUIRE(level + 1 < (uint32_t)MSM_MAX_LEVELS, "too many keyed-reduction levels");
-        if (count > 32768u) {
+        if (count > (g_msm_quad ? g_msm_quad_max : 32768u)) {
             // throughput regime: sequential chunks, one addition per entry
             const uint32_t L = count > (uint32_t)c.sm_count * 4096u ? 16u : 4u;
             const uint32_t nthreads = (count + L - 1) / L;
-            msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, run, level, L, buckets, keysB, ptsB);
+            msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, L, buckets, keysB, ptsB);
             ZK_LAUNCH_CHECK();
             count = nthreads;
+        } else if (g_msm_quad) {
+            // latency regime: one entry per quad, 8x per level, additions four multiplications deep
+            const uint32_t nwarps = (count + 7) / 8;
+            msm_combine_quad_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, buckets, keysB, ptsB);
+            ZK_LAUNCH_CHECK();
+            if (nwarps == 1) break;
+            count = nwarps;
         } else {
             const uint32_t nwarps = (count + 31) / 32;
-            msm_combine_warp_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, run, level, buckets, keysB, ptsB);
+            msm_combine_warp_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, buckets, keysB, ptsB);
             ZK_LAUNCH_CHECK();
             if (nwarps == 1) break;
             count = nwarps;
@@ -902,7 +1002,7 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
                                                                        buckets, keyA, ptA);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_COMBINE);
-    run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, run, buckets, s);
+    run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, run->level_count, buckets, s);
 
     if (!part.last) {
         T.mark(MSM_ST_END);
@@ -910,7 +1010,17 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     }
     // ---- 5: per-bucket-set running sums, then keyed reduction with key = bucket set
     T.mark(MSM_ST_REDUCE);
-    {
+    if (g_msm_quad) {
+        uint32_t lo_bits = 0;
+        while (lo_bits < 32 && (((uint64_t)(segs_per_group - 1) * seglen) >> lo_bits) != 0) ++lo_bits;
+        const uint32_t nthreads = (uint32_t)red_entries * 4;
+        msm_reduce_quad_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(buckets, nb, seglen, segs_per_group, (uint32_t)groups,
+                                                                      lo_bits, run->level_count2, keyA, ptA);
+        ZK_LAUNCH_CHECK();
+        T.mark(MSM_ST_REDUCE_COMBINE);
+        // per bucket set: the segment partials (key = bucket set, sorted) by the same keyed reduction, into `win`
+        run_combine_levels(c, keyA, ptA, keyB, ptB, (uint32_t)red_entries, run->level_count2, win, s);
+    } else {
         const uint32_t nthreads = (uint32_t)red_entries;
         msm_reduce_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(buckets, nb, seglen, segs_per_group, (uint32_t)groups,
                                                                  keyA, ptA);

@@ -677,6 +677,7 @@ def main() -> None:
             cpu_baseline["same_commitment_as_gpu"] = bool(msm_matches)
             # ... and of the transform: best_fft of the same 2^k scalars, element for element
             d_chk = d_scal.clone()
+            torch.cuda.synchronize()          # the clone runs on torch's stream, the transform on the library's
             b200zk.check(lib.b200zk_ntt_dev(vp(d_chk), n, 1, k, _ptr(omega), None, None))
             torch.cuda.synchronize()
             gpu_fft = d_chk.cpu().numpy().view(np.uint64).reshape(n, 4)

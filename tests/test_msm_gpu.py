@@ -252,10 +252,12 @@ def test_two_commits_on_two_streams_run_concurrently_and_agree(zk):
     torch.cuda.synchronize()
     w = fr1(omega_for(k))
     ntt_ref = sa.clone()
+    torch.cuda.synchronize()
     zk.check(lib.b200zk_ntt_dev(vp(ntt_ref), n, 1, k, C.c_void_p(w.ctypes.data), None, None))
     torch.cuda.synchronize()
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     p1, p2 = C.c_void_p(s1.cuda_stream), C.c_void_p(s2.cuda_stream)
+    canon = lambda t: zk.g1_to_bytes(np.ascontiguousarray(t.cpu().numpy().view(np.uint64).reshape(-1, 12)))
     for rep in range(4):
         got = torch.zeros(4, 12, dtype=torch.int64, device="cuda")
         t1, t2 = sa.clone(), sb.clone()
@@ -267,7 +269,8 @@ def test_two_commits_on_two_streams_run_concurrently_and_agree(zk):
         zk.check(lib.b200zk_ntt_dev(vp(t1), n, 1, k, C.c_void_p(w.ctypes.data), None, p1))
         zk.check(lib.b200zk_msm_g1_registered_dev(h.value, vp(sa), n, 1, n, vp(got[0]), p2))
         torch.cuda.synchronize()
-        assert torch.equal(got, ref), rep
+        # Jacobian coordinates depend on the (atomic) order of the pairs inside a bucket: compare the points
+        assert np.array_equal(canon(got), canon(ref)), rep
         assert torch.equal(t1, ntt_ref), rep
     exp = jac_affine(co.best_multiexp(co.gen_scalars(1, n), pts))
     assert jac_affine(ref[0].cpu().numpy().view(np.uint64)) == exp and jac_affine(ref[2].cpu().numpy().view(np.uint64)) == exp

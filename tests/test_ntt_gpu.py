@@ -43,6 +43,7 @@ def test_best_fft_vs_oracle_at_benchmark_sizes(zk, k):
     w = omega_for(k)
     exp = co.best_fft(a, fr1(w), k)
     dev = torch.from_numpy(a.view(np.int64).reshape(-1)).cuda()
+    torch.cuda.synchronize()              # torch's stream and the library's are not ordered
     zk.check(lib.b200zk_ntt_dev(C.c_void_p(dev.data_ptr()), n, 1, k, C.c_void_p(fr1(w).ctypes.data), None, None))
     torch.cuda.synchronize()
     assert np.array_equal(dev.cpu().numpy().view(np.uint64).reshape(n, 4), exp)
