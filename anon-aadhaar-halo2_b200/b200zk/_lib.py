@@ -11,7 +11,10 @@ from pathlib import Path
 
 PKG_ROOT = Path(__file__).resolve().parent.parent
 REPO_ROOT = PKG_ROOT.parent
-LIB_PATH = PKG_ROOT / "lib" / "libb200zk.so"
+import os
+
+# B200ZK_LIB_PATH: an experimental build (build.py --variant) for A/B measurements
+LIB_PATH = Path(os.environ["B200ZK_LIB_PATH"]) if os.environ.get("B200ZK_LIB_PATH") else PKG_ROOT / "lib" / "libb200zk.so"
 HEADER_PATH = REPO_ROOT / "include" / "b200zk.h"
 ABI_VERSION = 1
 

@@ -285,9 +285,11 @@ class ProverHotPath:
         check(lib.b200zk_gen_scalars_dev(C.c_void_p(self.instance_coeff.ptr), self.instance_coeff.n, self.seed + 3, 0))
         check(lib.b200zk_dev_download(self.lag.handle, 0, _ptr(self.h_lag), self.lag.n))
         check(lib.b200zk_dev_download(self.instance_coeff.handle, 0, _ptr(self.h_instance), self.instance_coeff.n))
-        check(lib.b200zk_mirror_enable(0))             # no mirror survives from the set-up above
         if mirror:
             check(lib.b200zk_mirror_enable(mirror_bytes))
+            check(lib.b200zk_mirror_invalidate(None, 0))   # a new proof: no mirror survives from the set-up above
+        else:
+            check(lib.b200zk_mirror_enable(0))
         col = lambda a, c, width: C.c_void_p(a.ctypes.data + c * width * 32)
         pp0 = s.advice + 2 * s.lookups
         lp0 = pp0 + s.permutation_sets
@@ -338,7 +340,7 @@ class ProverHotPath:
             st = (C.c_uint64 * 4)()
             check(lib.b200zk_mirror_stats(st))
             self.mirror_stats = {"hits": int(st[0]), "misses": int(st[1]), "resident_bytes": int(st[2]), "evictions": int(st[3])}
-            check(lib.b200zk_mirror_enable(0))
+            check(lib.b200zk_mirror_invalidate(None, 0))   # the pool of device blocks stays for the next proof
         return t
 
     def percall_counts(self) -> dict:
@@ -600,6 +602,7 @@ class ProverHotPath:
         if getattr(self, "host_advice", None) is not None:
             host_free(self.host_advice)
             self.host_advice = None
+        self.lib.b200zk_mirror_enable(0)
         if getattr(self, "_percall_pinned", False):
             for name in ("h_lag", "h_instance", "h_prod_ext", "h_values", "h_hcoeff"):
                 host_free(getattr(self, name))

@@ -32,6 +32,31 @@ def _stale(target: Path, deps) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def build_variant(name: str, defines) -> Path:
+    """An experimental build with extra -D flags into lib/libb200zk_<name>.so (objects in build/<name>/);
+    pick it at run time with B200ZK_LIB_PATH (b200zk/_lib.py).  Used for A/B measurements only."""
+    obj_dir = OBJ / name
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    LIB.parent.mkdir(exist_ok=True)
+    out = LIB.parent / f"libb200zk_{name}.so"
+    flags = FLAGS + [f"-D{d}" for d in defines]
+    sources = sorted(CSRC.glob("*.cu"))
+
+    def one(src):
+        r = subprocess.run([NVCC, *flags, "-c", str(src), "-o", str(obj_dir / (src.stem + ".o"))], capture_output=True, text=True)
+        (obj_dir / (src.stem + ".log")).write_text(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+
+    with cf.ThreadPoolExecutor(max_workers=8) as ex:
+        list(ex.map(one, sources))
+    r = subprocess.run([NVCC, "-shared", "-o", str(out), *[str(obj_dir / (x.stem + ".o")) for x in sources], "-lcudart"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     LIB.parent.mkdir(exist_ok=True)
@@ -67,4 +92,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:       # python build.py --variant NAME -DX=1 -DY=2
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

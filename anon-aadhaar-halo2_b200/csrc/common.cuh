@@ -249,6 +249,7 @@ struct MirrorCache {
         }
     }
     void release() {
+        hits = misses = evictions = 0;
         for (void* p : slabs) cudaFree(p);
         slabs.clear();
         entries.clear();

@@ -200,7 +200,12 @@ int b200zk_mirror_enable(size_t max_bytes) {
 int b200zk_mirror_invalidate(const void* host_ptr, size_t bytes) {
     return guarded([&] {
         Context& c = ctx();
-        if (!c.mirrors.enabled || !host_ptr) return;
+        if (!c.mirrors.enabled) return;
+        if (!host_ptr) {                           // forget every mirror; the device blocks stay pooled
+            while (!c.mirrors.entries.empty()) c.mirrors.drop(c.mirrors.entries.begin());
+            c.mirrors.hits = c.mirrors.misses = c.mirrors.evictions = 0;
+            return;
+        }
         // the library stream may still be reading the mirror (host-pointer calls are synchronous, so it is
         // idle here); freed blocks are only ever reused by work queued later on that stream
         c.mirrors.invalidate(host_ptr, bytes);

@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint32_t* bsum,
 // level.  The host launches grids for the worst case; threads beyond the planned counts exit.
 constexpr int MSM_MAX_LEVELS = 12;
 struct MsmRun {
-    uint32_t npairs, L, nthreads, pad;
+    uint32_t npairs, L, nthreads;
+    uint32_t any_long;   // some bucket has more open partial sums than the direct finish takes: run the keyed levels
     uint32_t level_count[MSM_MAX_LEVELS];   // entries entering combine level l (bucket accumulation)
     uint32_t level_count2[MSM_MAX_LEVELS];  // the same for the keyed reduction of the bucket-segment partials
 };
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __rest
         run->npairs = np;
         run->L = L;
         run->nthreads = (np + L - 1) / L;
+        run->any_long = 0;
         run->level_count[0] = run->nthreads;
     }
 }
@@ -388,7 +390,9 @@ __global__ void __launch_bounds__(128, 5) msm_accum_kernel(const G1Affine* __res
 __global__ void __launch_bounds__(128) msm_combine_kernel(const uint32_t* __restrict__ keys, const G1Xyzz* __restrict__ pts,
                                                           uint32_t* __restrict__ counts, uint32_t level, uint32_t L,
                                                           G1Xyzz* __restrict__ buckets,
-                                                          uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt) {
+                                                          uint32_t* __restrict__ carry_key, G1Xyzz* __restrict__ carry_pt,
+                                                          const uint32_t* __restrict__ enabled) {
+    if (enabled && !*enabled) return;                // the direct finish has already closed every run
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t count = counts[level];
     const uint32_t nthreads = (count + L - 1) / L;
@@ -443,7 +447,9 @@ __global__ void __launch_bounds__(128) msm_combine_warp_kernel(const uint32_t* _
                                                                const G1Xyzz* __restrict__ pts, uint32_t* __restrict__ counts,
                                                                uint32_t level, G1Xyzz* __restrict__ buckets,
                                                                uint32_t* __restrict__ carry_key,
-                                                               G1Xyzz* __restrict__ carry_pt) {
+                                                               G1Xyzz* __restrict__ carry_pt,
+                                                               const uint32_t* __restrict__ enabled) {
+    if (enabled && !*enabled) return;
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t count = counts[level];
     if (gid == 0) counts[level + 1] = (count + 31) / 32;
@@ -490,7 +496,9 @@ __global__ void __launch_bounds__(128) msm_combine_quad_kernel(const uint32_t* _
                                                                const G1Xyzz* __restrict__ pts, uint32_t* __restrict__ counts,
                                                                uint32_t level, G1Xyzz* __restrict__ buckets,
                                                                uint32_t* __restrict__ carry_key,
-                                                               G1Xyzz* __restrict__ carry_pt) {
+                                                               G1Xyzz* __restrict__ carry_pt,
+                                                               const uint32_t* __restrict__ enabled) {
+    if (enabled && !*enabled) return;
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t role = threadIdx.x & 3u, qlane = (threadIdx.x & 31u) >> 2;
     const uint32_t count = counts[level];
@@ -524,6 +532,47 @@ __global__ void __launch_bounds__(128) msm_combine_quad_kernel(const uint32_t* _
     if (head && reaches_end && role == 0) {
         carry_key[warp] = key;
         st_xyzz(carry_pt + warp, open ? v : G1Xyzz::identity());
+    }
+}
+
+// Direct finish of the bucket accumulation (one quad per bucket).  The open partial sums the accumulation
+// handed up for bucket b sit at consecutive thread indices that follow from the bucket offsets alone:
+// thread t's last pair is at position min((t + 1) L, npairs) - 1, so bucket [s, e) owns t in [s / L, e / L)
+// (through the last thread when e = npairs).  With uniform scalars that is a handful per bucket; the quad
+// adds them up and folds them into the bucket, and no keyed-reduction level has to run.  A bucket with more
+// than `rmax` partials (skewed scalars: every point of a window in one bucket) raises run->any_long and is left to
+// the keyed levels, which then run over the whole list; the partials consumed here are cleared so that they
+// count once.
+__global__ void __launch_bounds__(128) msm_finish_quad_kernel(const uint32_t* __restrict__ start, uint32_t nkeys,
+                                                              MsmRun* __restrict__ run, uint32_t rmax,
+                                                              G1Xyzz* __restrict__ buckets, G1Xyzz* __restrict__ carry_pt) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t role = threadIdx.x & 3u;
+    const uint32_t q = gid >> 2;
+    const bool live = q < nkeys;
+    const uint32_t b = live ? q : nkeys - 1;
+    const uint32_t L = run->L, npairs = run->npairs, nthreads = run->nthreads;
+    const uint32_t s = __ldg(start + b), e = __ldg(start + b + 1);
+    const uint32_t t0 = s / L, t1 = (e == npairs) ? nthreads : e / L;
+    uint32_t r = (live && e > s) ? t1 - t0 : 0u;
+    if (r > rmax) {
+        if (role == 0) run->any_long = 1u;
+        r = 0;
+    }
+    const uint32_t steps = __reduce_max_sync(0xffffffffu, r);
+    G1Xyzz acc = G1Xyzz::identity();
+#pragma unroll 1
+    for (uint32_t i = 0; i < steps; ++i) {
+        const bool take = i < r;
+        G1Xyzz x = take ? ld_xyzz(carry_pt + t0 + i) : G1Xyzz::identity();
+        acc = quad_add(acc, x, role);
+        if (take && role == 0) st_fq(&carry_pt[t0 + i].zz, Fq::zero());      // consumed
+    }
+    const bool need = r > 0 && !acc.is_identity();
+    if (__any_sync(0xffffffffu, need)) {
+        G1Xyzz bk = need ? ld_xyzz(buckets + b) : G1Xyzz::identity();
+        bk = quad_add(bk, acc, role);
+        if (need && role == 0) st_xyzz(buckets + b, bk);
     }
 }
 
@@ -804,31 +853,49 @@ struct MsmPre {
 // added into `buckets`.  Small inputs use short chunks: the cost of a level is the latency
 // of L dependent point additions, not throughput.
 static bool g_msm_quad = getenv("B200ZK_MSM_QUAD") ? atoi(getenv("B200ZK_MSM_QUAD")) != 0 : true;
+static uint32_t g_msm_finish_max = getenv("B200ZK_MSM_FINISH_MAX") ? (uint32_t)atoi(getenv("B200ZK_MSM_FINISH_MAX")) : 48u;
+static size_t g_msm_quad_reduce_max = getenv("B200ZK_MSM_QUAD_REDUCE_MAX") ? (size_t)atoll(getenv("B200ZK_MSM_QUAD_REDUCE_MAX")) : ((size_t)1 << 14);
+static uint32_t g_msm_finish_max_threads = getenv("B200ZK_MSM_FINISH_MAX_THREADS") ? (uint32_t)atoi(getenv("B200ZK_MSM_FINISH_MAX_THREADS")) : (1u << 19);
 static uint32_t g_msm_quad_max = getenv("B200ZK_MSM_QUAD_MAX") ? (uint32_t)atoi(getenv("B200ZK_MSM_QUAD_MAX")) : (1u << 17);
 
 static void run_combine_levels(Context& c, uint32_t* keysA, G1Xyzz* ptsA, uint32_t* keysB, G1Xyzz* ptsB,
-                               uint32_t count, uint32_t* counts, G1Xyzz* buckets, cudaStream_t s) {
+                               uint32_t count, uint32_t* counts, G1Xyzz* buckets, cudaStream_t s,
+                               const uint32_t* enabled = nullptr) {
     // `count` bounds the entries of level 0; the exact counts are in counts[level] (device)
     uint32_t level = 0;
     while (count > 0) {
         ZK_REQUIRE(level + 1 < (uint32_t)MSM_MAX_LEVELS, "too many keyed-reduction levels");
-        if (count > (g_msm_quad ? g_msm_quad_max : 32768u)) {
+        if (enabled && count > 1024u) {
+            // behind the direct finish these levels only run for skewed scalars (a bucket longer than the
+            // finish takes); otherwise each is an empty launch, so shrink fast: 16x, then 32x per level
+            const uint32_t L = 16u;
+            const uint32_t nthreads = (count + L - 1) / L;
+            msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, L, buckets, keysB, ptsB, enabled);
+            ZK_LAUNCH_CHECK();
+            count = nthreads;
+        } else if (enabled) {
+            const uint32_t nwarps = (count + 31) / 32;
+            msm_combine_warp_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, buckets, keysB, ptsB, enabled);
+            ZK_LAUNCH_CHECK();
+            if (nwarps == 1) break;
+            count = nwarps;
+        } else if (count > (g_msm_quad ? g_msm_quad_max : 32768u)) {
             // throughput regime: sequential chunks, one addition per entry
             const uint32_t L = count > (uint32_t)c.sm_count * 4096u ? 16u : 4u;
             const uint32_t nthreads = (count + L - 1) / L;
-            msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, L, buckets, keysB, ptsB);
+            msm_combine_kernel<<<(nthreads + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, L, buckets, keysB, ptsB, enabled);
             ZK_LAUNCH_CHECK();
             count = nthreads;
         } else if (g_msm_quad) {
             // latency regime: one entry per quad, 8x per level, additions four multiplications deep
             const uint32_t nwarps = (count + 7) / 8;
-            msm_combine_quad_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, buckets, keysB, ptsB);
+            msm_combine_quad_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, buckets, keysB, ptsB, enabled);
             ZK_LAUNCH_CHECK();
             if (nwarps == 1) break;
             count = nwarps;
         } else {
             const uint32_t nwarps = (count + 31) / 32;
-            msm_combine_warp_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, buckets, keysB, ptsB);
+            msm_combine_warp_kernel<<<(nwarps * 32 + 127) / 128, 128, 0, s>>>(keysA, ptsA, counts, level, buckets, keysB, ptsB, enabled);
             ZK_LAUNCH_CHECK();
             if (nwarps == 1) break;
             count = nwarps;
@@ -1002,7 +1069,15 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
                                                                        buckets, keyA, ptA);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_COMBINE);
-    run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, run->level_count, buckets, s);
+    if (g_msm_quad && nthreads0 <= g_msm_finish_max_threads) {
+        // latency regime (a single small commit): every bucket's open partials by one quad; the keyed levels below
+        // only run when a bucket was too long for it.  (At 2^24 the levels are cheaper: 0.64 ms against 1.56 ms.)
+        msm_finish_quad_kernel<<<(nkeys * 4u + 127u) / 128u, 128, 0, s>>>(start, nkeys, run, g_msm_finish_max, buckets, ptA);
+        ZK_LAUNCH_CHECK();
+        run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, run->level_count, buckets, s, &run->any_long);
+    } else {
+        run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, run->level_count, buckets, s);
+    }
 
     if (!part.last) {
         T.mark(MSM_ST_END);
@@ -1010,7 +1085,9 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     }
     // ---- 5: per-bucket-set running sums, then keyed reduction with key = bucket set
     T.mark(MSM_ST_REDUCE);
-    if (g_msm_quad) {
+    // quads for the latency regime; a batch of columns or a 2^24-point commit has enough segments to keep the
+    // multipliers busy with one lane per segment, which does ~1.5x less work
+    if (g_msm_quad && red_entries <= g_msm_quad_reduce_max) {
         uint32_t lo_bits = 0;
         while (lo_bits < 32 && (((uint64_t)(segs_per_group - 1) * seglen) >> lo_bits) != 0) ++lo_bits;
         const uint32_t nthreads = (uint32_t)red_entries * 4;

@@ -22,7 +22,16 @@
 
 namespace zk {
 
-constexpr int NTT_TILE_LOG = 11;             // 2048 elements per CTA
+#ifndef B200ZK_NTT_TILE_LOG
+#define B200ZK_NTT_TILE_LOG 11
+#endif
+// resident CTAs per SM the pass kernel is compiled for.  Measured on B200 (scratch/r2_ntt_sweep.py): 3 (80
+// registers, ~350 B of spills, 24 warps per SM) beats 2 (112 registers, no spills) at every size — 4.11 -> 3.86 ms
+// at 2^24, 1.18 -> 1.11 ms for 242 transforms of 2^15 — and 1024-element tiles with 4 or 5 CTAs are slower (4.36 ms).
+#ifndef B200ZK_NTT_MIN_CTAS
+#define B200ZK_NTT_MIN_CTAS 3
+#endif
+constexpr int NTT_TILE_LOG = B200ZK_NTT_TILE_LOG;   // 2048 elements per CTA
 constexpr int NTT_TILE = 1 << NTT_TILE_LOG;
 constexpr int NTT_THREADS = NTT_TILE / 8;    // 256
 constexpr int NTT_MAX_B = 9;
@@ -321,7 +330,7 @@ __device__ __forceinline__ void ntt_rounds_from(const NttPassArgs& A, const Fr* 
 }
 
 template <int B, bool FIRST>
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(const __grid_constant__ NttPassArgs A) {
+__global__ void __launch_bounds__(NTT_THREADS, B200ZK_NTT_MIN_CTAS) ntt_pass_kernel(const __grid_constant__ NttPassArgs A) {
     extern __shared__ uint4 ntt_smem[];
     uint4* S0 = ntt_smem;
     uint4* S1 = ntt_smem + NTT_TILE;

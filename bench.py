@@ -309,15 +309,26 @@ def run_reference(args) -> None:
 
 
 def ntt_modmul_per_element(k: int) -> float:
-    """Multiplications per element of one 2^k transform as csrc/ntt.cu plans it: k/2 for the butterflies, and
-    per pass boundary one (a single table of the boundary's 2^(k - log_I) twiddles, used up to 2^20 entries) or
-    two (lo / hi tables)."""
+    """Field multiplications per element that csrc/ntt.cuh actually executes for one 2^k transform (counted from
+    the kernel, not k/2 + twiddles): per pass of 2^b rows the rounds are radix 8, 8, ..., then 2^(b mod 3); a
+    radix-8 round multiplies 5 of its 12 butterfly outputs (the others meet the trivial root), a radix-4 round 1 of
+    4; between rounds every element whose digit c and lower index lo are both non-zero takes one in-tile twiddle;
+    a pass boundary costs one multiplication per element with a direct table (boundaries of <= 2^20 twiddles) and
+    two with the lo / hi tables.  12.0 at k = 24 — what radix-2 needs (k/2), not more."""
     npass = max(1, -(-k // 9))
     bits = [k // npass + (1 if p < k % npass else 0) for p in range(npass)]
-    per, log_i = k / 2, 0
-    for p in range(npass - 1):
-        per += 1 if k - log_i <= 20 else 2
-        log_i += bits[p]
+    per, log_i = 0.0, 0
+    for p, b in enumerate(bits):
+        rounds = [3] * (b // 3) + ([b % 3] if b % 3 else [])
+        for q, r in enumerate(rounds):
+            per += {3: 5 / 8, 2: 1 / 4, 1: 0.0}[r]
+            later = sum(rounds[q + 1:])
+            if q + 1 < len(rounds):
+                per += (1 - 2.0 ** -r) * (1 - 2.0 ** -later)
+        if p + 1 < npass:
+            nonzero = (1 - 2.0 ** -b) * (1 - 2.0 ** -(k - log_i - b))     # exponent i_p * J is zero when either is
+            per += (1 if k - log_i <= 20 else 2) * nonzero
+        log_i += b
     return per
 
 
@@ -553,7 +564,7 @@ def main() -> None:
         "int_frac": ntt_modmul / peak_modmul,
         "traffic": traffic.get(f"ntt@k{k}"),
         "note": "254-bit butterflies make the transform integer-bound on B200: int_frac is the fraction of the "
-                "measured modmul peak (k/2 butterfly multiplications per element + 1 or 2 twiddle multiplications per pass boundary)",
+                "measured modmul peak, counting only the multiplications the kernel executes (ntt_modmul_per_element: 12.0 per element at k = 24)",
     }
 
     # ---- the same MSM through plain best_multiexp (bases per call, no window table)

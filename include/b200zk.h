@@ -69,7 +69,8 @@ int b200zk_host_free(void* ptr);
  * what it wrote; later calls on the same buffer skip the upload (b200zk_dev_upload copies device to
  * device).  Results are the same bytes either way.  The contract that makes this sound: while mirrors
  * are on, the caller calls b200zk_mirror_invalidate(ptr, bytes) before it writes or frees host memory
- * it has passed to a host-pointer call (bytes = 0: whatever mirror contains `ptr`).  The Rust fork
+ * it has passed to a host-pointer call (bytes = 0: whatever mirror contains `ptr`; ptr = NULL: every
+ * mirror, e.g. between proofs — the device blocks stay pooled and the statistics restart).  The Rust fork
  * keeps that contract inside `Polynomial` (a `Cell<bool>` set when the buffer is handed to the
  * library, checked in `DerefMut` and `Drop`) and invalidates immediately after a call on a plain
  * slice (`best_multiexp`, `best_fft`), see INTEGRATION.md.  Least-recently-used mirrors are dropped
