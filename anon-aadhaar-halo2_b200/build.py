@@ -57,7 +57,24 @@ def build_variant(name: str, defines) -> Path:
     return out
 
 
+WITNESS_LIB = PKG / "lib" / "libb200zk_witness.so"
+
+
+def build_witness(force: bool = False) -> Path:
+    """The host-only witness generator (host/witness_rsa.cpp, include/b200zk_witness.h): g++, no CUDA."""
+    src = PKG / "host" / "witness_rsa.cpp"
+    hdr = PKG.parent / "include" / "b200zk_witness.h"
+    WITNESS_LIB.parent.mkdir(exist_ok=True)
+    if force or _stale(WITNESS_LIB, [src, hdr]):
+        r = subprocess.run([os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", str(src),
+                            "-o", str(WITNESS_LIB)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+    return WITNESS_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    build_witness(force)
     OBJ.mkdir(exist_ok=True)
     LIB.parent.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "b200zk.h"]

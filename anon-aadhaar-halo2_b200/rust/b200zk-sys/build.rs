@@ -1,5 +1,5 @@
 // Either link a prebuilt libb200zk.so (B200ZK_LIB_DIR) or compile the CUDA sources with nvcc
-// through the `cc` crate.  No bindgen: the ABI is ~35 functions, declared by hand in lib.rs.
+// through the `cc` crate.  No bindgen: the ABI is ~75 functions, declared by hand in lib.rs.
 use std::{env, path::PathBuf};
 
 fn main() {
@@ -14,7 +14,7 @@ fn main() {
         .cuda(true)
         .flag("-gencode").flag("arch=compute_100a,code=sm_100a")
         .flag("-O3").flag("-lineinfo").flag("-std=c++17").flag("--expt-relaxed-constexpr")
-        .files(["core.cu", "ntt.cu", "msm.cu", "quotient.cu"].iter().map(|f| csrc.join(f)))
+        .files(["core.cu", "ntt.cu", "msm.cu", "quotient.cu", "poly.cu", "permute.cu", "encoding.cu"].iter().map(|f| csrc.join(f)))
         .compile("b200zk");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rerun-if-changed={}", csrc.display());

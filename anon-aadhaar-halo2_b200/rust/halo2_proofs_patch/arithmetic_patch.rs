@@ -19,6 +19,8 @@ pub fn best_multiexp<C: CurveAffine>(coeffs: &[C::Scalar], bases: &[C]) -> C::Cu
         ffi::check(unsafe {
             ffi::b200zk_msm_g1(coeffs.as_ptr() as *const u64, bases.as_ptr() as *const u64, coeffs.len(), out.as_mut_ptr())
         });
+        // a plain slice carries no mirror flag: if mirrors are on, forget what this call uploaded
+        unsafe { ffi::b200zk_mirror_invalidate(coeffs.as_ptr() as *const core::ffi::c_void, 0) };
         // SAFETY: C::Curve == G1 here; [u64; 12] is its in-memory representation.
         return unsafe { transmute_copy::<[u64; 12], C::Curve>(&out) };
     }
@@ -30,6 +32,7 @@ pub fn best_fft<G: Group>(a: &mut [G], omega: G::Scalar, log_n: u32) {
     assert_eq!(a.len(), 1 << log_n);
     if TypeId::of::<G>() == TypeId::of::<Fr>() {
         ffi::check(unsafe { ffi::b200zk_ntt(a.as_mut_ptr() as *mut u64, log_n, &omega as *const _ as *const u64) });
+        unsafe { ffi::b200zk_mirror_invalidate(a.as_ptr() as *const core::ffi::c_void, 0) };   // `&mut [G]`: no flag to keep it coherent
         return;
     }
     upstream::best_fft(a, omega, log_n)
@@ -40,6 +43,9 @@ impl<G: Group> EvaluationDomain<G> {
     pub fn lagrange_to_coeff(&self, mut a: Polynomial<G, LagrangeCoeff>) -> Polynomial<G, Coeff> {
         assert_eq!(a.values.len(), 1 << self.k);
         if TypeId::of::<G>() == TypeId::of::<Fr>() {
+            // `a.values` is touched through the field, not through DerefMut: a mirror left by commit_lagrange(&a)
+            // stays valid, the transform runs in it and leaves it equal to what it writes back (poly_patch.rs)
+            a.mark_mirrored();
             ffi::check(unsafe {
                 ffi::b200zk_intt(a.values.as_mut_ptr() as *mut u64, self.k,
                                  &self.omega_inv as *const _ as *const u64, &self.ifft_divisor as *const _ as *const u64)
@@ -47,20 +53,22 @@ impl<G: Group> EvaluationDomain<G> {
         } else {
             Self::ifft(&mut a.values, self.omega_inv, self.k, self.ifft_divisor);
         }
-        Polynomial { values: a.values, _marker: PhantomData }
+        a.rebase()
     }
 
     /// `EvaluationDomain::coeff_to_extended` — zeta shift, zero padding and NTT fused.
     pub fn coeff_to_extended(&self, a: Polynomial<G, Coeff>) -> Polynomial<G, ExtendedLagrangeCoeff> {
         assert_eq!(a.values.len(), 1 << self.k);
         if TypeId::of::<G>() == TypeId::of::<Fr>() {
-            let mut out = vec![G::group_zero(); self.extended_len()];
+            let mut out = Polynomial::from_values(vec![G::group_zero(); self.extended_len()]);
+            a.mark_mirrored();
+            out.mark_mirrored();          // the library keeps the extended column for evaluate_h
             ffi::check(unsafe {
-                ffi::b200zk_coeff_to_extended(a.values.as_ptr() as *const u64, self.k, out.as_mut_ptr() as *mut u64,
+                ffi::b200zk_coeff_to_extended(a.values.as_ptr() as *const u64, self.k, out.values.as_mut_ptr() as *mut u64,
                                               self.extended_k, &self.extended_omega as *const _ as *const u64,
                                               &self.g_coset as *const _ as *const u64)
             });
-            return Polynomial { values: out, _marker: PhantomData };
+            return out;
         }
         upstream::coeff_to_extended(self, a)
     }
@@ -96,25 +104,9 @@ impl<G: Group> EvaluationDomain<G> {
     }
 }
 
-// poly/kzg/commitment.rs: ParamsKZG<Bn256> gains two private fields holding the handles returned by
-// b200zk_bases_register(g) / (g_lagrange) at construction (`setup`, `read`, `downsize` re-register),
-// and a Drop impl calling b200zk_bases_evict.  Bodies:
-//
-//   fn commit(&self, poly: &Polynomial<Fr, Coeff>, _: Blind<Fr>) -> G1 {
-//       let mut out = [0u64; 12];
-//       ffi::check(unsafe { ffi::b200zk_msm_g1_registered(self.g_handle, poly.as_ptr() as *const u64, poly.len(), out.as_mut_ptr()) });
-//       unsafe { transmute::<[u64; 12], G1>(out) }
-//   }
-//   fn commit_lagrange(..)  — same with self.g_lagrange_handle.
-//
-// plonk/evaluation.rs: Evaluator::evaluate_h flattens self.custom_gates / self.lookups[n] into
-// b200zk_graph (ValueSource / Calculation discriminants are the `kind` / `op` numbers documented in
-// include/b200zk.h), keeps pk.fixed_cosets, pk.l0 / l_last / l_active_row and pk.permutation.cosets
-// resident through b200zk_dev_alloc + b200zk_dev_upload at keygen time, extends advice / instance /
-// lookup / permutation-product polynomials with b200zk_coeff_to_extended_dev into device columns, and
-// calls b200zk_quotient_graph, b200zk_quotient_permutation and b200zk_quotient_lookup in upstream's
-// loop order; the result is downloaded into `values` (or kept resident for vanishing::construct,
-// which then calls b200zk_extended_to_coeff_dev with t_evaluations fused).
+// poly/kzg/commitment.rs (`ParamsKZG::{commit, commit_lagrange, Drop}` and the handle fields): commitment_patch.rs
+// plonk/evaluation.rs (`Evaluator::evaluate_h`, the flattened `GraphEvaluator`, the device-resident key): evaluation_patch.rs
+// poly.rs (`Polynomial` with the mirror flag that keeps b200zk_mirror_* coherent): poly_patch.rs
 
 // ---- the loops either side of the hot path (SURVEY.md section 8 f) ---------------------------
 
