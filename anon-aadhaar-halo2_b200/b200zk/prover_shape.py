@@ -464,8 +464,9 @@ class ProverHotPath:
         self.cosets_per_rank = -(-self.parts // world)
         self.col_b, self.col_e = shard_range(self.n_lag, rank, world)
         self.maxc = -(-self.n_lag // world)
-        # padded copy of the Lagrange columns so every rank's block has maxc columns
+        # every rank holds the Lagrange columns (the witness); `coef_mine` is its share of them in coefficient form
         self.lag_pad = DeviceColumn((self.n_lag + self.maxc) * n)
+        self.coef_mine = DeviceColumn(self.maxc * n)
         self.coef_all = DeviceColumn(world * self.maxc * n)
         self.cos = DeviceColumn((world * self.maxc + s.instance) * n)
         self.cos_views = [DeviceColumn.view(self.cos, i * n, n) for i in range(world * self.maxc + s.instance)]
@@ -485,11 +486,62 @@ class ProverHotPath:
             self.col_pos += [r * self.maxc + (cidx - b) for cidx in range(b, e)]
         from .api import FR_MODULUS
         self.coset_gen = [fr_limbs(FR_ZETA * pow(d.extended_omega_int, q, FR_MODULUS) % FR_MODULUS) for q in range(self.parts)]
+        # ---- the commitments are dealt by *load*: a rank that evaluates cosets of h(X), and rank 0 which also finishes
+        # h(X), gets fewer columns to commit, so that all ranks finish together.  Cost model in ms (per column, per coset,
+        # the finish on rank 0); rebalance() replaces it with what the last run measured.
+        self.cost = {"column": [0.125] * world, "fixed": [3.3 * len(range(r, self.parts, world)) + (1.3 if r == 0 else 0.0)
+                                                           for r in range(world)]}
+        self._deal_commits()
+
+    def _deal_commits(self) -> None:
+        """Column counts x_r with fixed_r + column_r * x_r equal for all ranks (water filling), sum = n_lag."""
+        world, total = self.world, self.n_lag
+        col, fixed = self.cost["column"], self.cost["fixed"]
+        lo, hi = min(fixed), max(fixed) + max(col) * total
+        for _ in range(60):                                  # the finish time t at which sum_r max(0, (t - fixed_r) / col_r) = total
+            t = 0.5 * (lo + hi)
+            if sum(max(0.0, (t - fixed[r]) / col[r]) for r in range(world)) >= total:
+                hi = t
+            else:
+                lo = t
+        want = [max(0.0, (hi - fixed[r]) / col[r]) for r in range(world)]
+        counts = [int(w) for w in want]
+        for r in sorted(range(world), key=lambda r: want[r] - counts[r], reverse=True)[: total - sum(counts)]:
+            counts[r] += 1
+        self.commit_ranges, b = [], 0
+        for r in range(world):
+            self.commit_ranges.append((b, b + counts[r]))
+            b += counts[r]
+        assert b == total
+
+    def rebalance(self, torch, dist, t: dict) -> None:
+        """Replace the cost model by the last run's measurements (all ranks) and deal the commitments again."""
+        world = self.world
+        b, e = self.commit_ranges[self.rank]
+        mine = torch.tensor([t["commit_own_columns"] / max(1, e - b) if e > b else 0.0,
+                             t["coset_ntt_and_quotient_own_cosets"] + t.get("finish_h_on_rank0", 0.0)], dtype=torch.float64, device="cuda")
+        allv = torch.zeros(2 * world, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_gather_into_tensor(allv, mine)
+        else:
+            allv = mine
+        v = allv.cpu().tolist()
+        rates = [v[2 * r] for r in range(world) if v[2 * r] > 0]
+        default = sum(rates) / len(rates) if rates else 0.125
+        self.cost = {"column": [v[2 * r] if v[2 * r] > 0 else default for r in range(world)],
+                     "fixed": [v[2 * r + 1] for r in range(world)]}
+        self._deal_commits()
 
     def run_sharded(self, torch, dist=None) -> dict:
-        """The same proof as run(), spread over `world` ranks (prepare_sharded first).  world = 1
-        exercises the whole coset path on one GPU.  `torch` supplies the NCCL collectives and the
-        device copies around library-owned memory."""
+        """The same proof as run(), spread over `world` ranks (prepare_sharded first).  world = 1 exercises the whole
+        coset path on one GPU.  `torch` supplies the NCCL collectives and the device copies around library-owned memory.
+
+        Schedule: (1) every rank takes its even share of the Lagrange columns to coefficient form (a copy: the Lagrange
+        columns are still to be committed) and the coefficient columns are all-gathered; (2) the ranks that own cosets
+        of the extended domain extend and evaluate them; the all-gather of the evaluated cosets is issued
+        asynchronously, so ranks without cosets do not wait for it; (3) every rank commits its load-weighted share of
+        the Lagrange columns; (4) rank 0, which has the fewest columns, finishes h(X) (interleave, divide,
+        extended_to_coeff, commit the pieces); (5) the commitments are gathered."""
         lib, s, d, n, N = self.lib, self.shape, self.domain, self.n, self.N
         world, rank = self.world, self.rank
         t, marks = {}, [time.perf_counter()]
@@ -505,20 +557,20 @@ class ProverHotPath:
         if world > 1:
             dist.barrier()
         marks[0] = time.perf_counter()
+        # ---- (1) own share -> coefficient form, all-gather
         b, e = self.col_b, self.col_e
-        mine = self.lag_pad.ptr + b * n * 32
         if e > b:
-            self._commit(mine, e - b, b)
-            check(lib.b200zk_ntt_dev(C.c_void_p(mine), n, e - b, d.k, _ptr(d.omega_inv), _ptr(d.ifft_divisor), None))
-        mark("commit_and_lagrange_to_coeff_own_columns")
+            self._torch_view(torch, self.coef_mine, 0, (e - b) * n).copy_(self._torch_view(torch, self.lag_pad, b * n, (e - b) * n))
+            self.sync()
+            check(lib.b200zk_ntt_dev(C.c_void_p(self.coef_mine.ptr), n, e - b, d.k, _ptr(d.omega_inv), _ptr(d.ifft_divisor), None))
+        mark("lagrange_to_coeff_own_columns")
         if world > 1:
             dist.all_gather_into_tensor(self._torch_view(torch, self.coef_all, 0, world * self.maxc * n),
-                                        self._torch_view(torch, self.lag_pad, b * n, self.maxc * n))
-            pts_all = torch.zeros(world * self.maxc * 12, dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(pts_all, self._torch_view(torch, self.points, b * 3, self.maxc * 3))
+                                        self._torch_view(torch, self.coef_mine, 0, self.maxc * n))
         else:
-            self._torch_view(torch, self.coef_all, 0, self.maxc * n).copy_(self._torch_view(torch, self.lag_pad, 0, self.maxc * n))
+            self._torch_view(torch, self.coef_all, 0, self.maxc * n).copy_(self._torch_view(torch, self.coef_mine, 0, self.maxc * n))
         mark("all_gather_coefficient_columns")
+        # ---- (2) own cosets of the extended domain
         env_scal = self.scalars
         zeta_delta = fr_limbs(FR_DELTA)
         for slot, q in enumerate(self.my_cosets):
@@ -564,9 +616,20 @@ class ProverHotPath:
                                                  l_last.handle, l_active.handle))
             values.free()
         mark("coset_ntt_and_quotient_own_cosets")
+        # the evaluated cosets travel to rank 0 while everybody commits: asynchronous, so a rank without cosets (it
+        # arrives here at once) does not wait for the ranks that have some
+        h_work = None
         if world > 1:
-            dist.all_gather_into_tensor(self._torch_view(torch, self.h_all, 0, world * self.cosets_per_rank * n),
-                                        self._torch_view(torch, self.h_mine, 0, self.cosets_per_rank * n))
+            h_work = dist.all_gather_into_tensor(self._torch_view(torch, self.h_all, 0, world * self.cosets_per_rank * n),
+                                                 self._torch_view(torch, self.h_mine, 0, self.cosets_per_rank * n), async_op=True)
+        # ---- (3) commitments of the Lagrange columns, dealt by load
+        cb, ce = self.commit_ranges[rank]
+        if ce > cb:
+            self._commit(self.lag_pad.ptr + cb * n * 32, ce - cb, cb)
+        mark("commit_own_columns")
+        # ---- (4) h(X) on rank 0
+        if h_work is not None:
+            h_work.wait()
         mark("gather_h_cosets")
         if rank == 0:
             for q in range(self.parts):
@@ -584,6 +647,18 @@ class ProverHotPath:
             self.sync()
             t_ev.free()
         mark("finish_h_on_rank0")
+        # ---- (5) every commitment on every rank (the transcript needs them on rank 0)
+        if world > 1:
+            width = max(ce_ - cb_ for cb_, ce_ in self.commit_ranges)
+            mine = torch.zeros(width * 12, dtype=torch.int64, device="cuda")
+            if ce > cb:
+                mine[: (ce - cb) * 12].copy_(self._torch_view(torch, self.points, cb * 3, (ce - cb) * 3))
+            allp = torch.zeros(world * width * 12, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(allp, mine)
+            for r, (rb, re_) in enumerate(self.commit_ranges):
+                if re_ > rb and r != rank:
+                    self._torch_view(torch, self.points, rb * 3, (re_ - rb) * 3).copy_(allp[r * width * 12: r * width * 12 + (re_ - rb) * 12])
+        mark("gather_commitments")
         if world > 1:
             dist.barrier()
         t["total"] = 1e3 * (time.perf_counter() - marks[0])
@@ -615,7 +690,7 @@ class ProverHotPath:
             col.free()
         for v in getattr(self, "cos_views", []):
             v.free()
-        for name in ("lag_pad", "coef_all", "cos", "h_mine", "h_all", "coef"):
+        for name in ("lag_pad", "coef_mine", "coef_all", "cos", "h_mine", "h_all", "coef"):
             if hasattr(self, name):
                 getattr(self, name).free()
         for c in (self.pk_cols, self.lag, self.instance_coeff, self.ext, self.values, self.table, self.h_coeff,

@@ -164,9 +164,14 @@ class DeviceFourStep:
         if world > 1 and mode in ("auto", "p2p"):
             try:
                 import torch.distributed._symmetric_memory as symm
-                self.rows = symm.empty(self.rows_elems * 4, dtype=torch.int64, device=device)
-                self.hdl = symm.rendezvous(self.rows, dist.group.WORLD.group_name)
-                self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+                # two row buffers, used alternately: a peer may still be reading the rows of the previous
+                # transform while this rank already stores into the other buffer, so the only barrier left is
+                # the one after the stores ("my rows are complete")
+                self.rows2 = [symm.empty(self.rows_elems * 4, dtype=torch.int64, device=device) for _ in range(2)]
+                self.hdl2 = [symm.rendezvous(r, dist.group.WORLD.group_name) for r in self.rows2]
+                self.peer_ptrs2 = [[int(p) for p in h.buffer_ptrs] for h in self.hdl2]
+                self.turn = 0
+                self.rows = self.rows2[0]
                 self.mode = "p2p"
             except Exception as e:   # no peer mapping available: fall back to the NCCL exchange
                 if mode == "p2p":
@@ -218,12 +223,16 @@ class DeviceFourStep:
         w = fr_limbs(omega)
         bases = (C.c_void_p * world)()
         if self.mode == "p2p":
-            self.hdl.barrier(channel=0)          # every peer is done reading its previous rows
+            # buffer `turn` was last read two transforms ago, and every rank has passed the barrier of the transform
+            # in between since then: it is free on every peer without another barrier
+            turn = self.turn
+            self.turn ^= 1
             for s in range(world):
-                bases[s] = self.peer_ptrs[s]
+                bases[s] = self.peer_ptrs2[turn][s]
             self.check(self.lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(buf.data_ptr()), k, log_n1, _ptr(w), world,
                                                                 rank, bases, n2, rank * m, self._stream()))
-            self.hdl.barrier(channel=1)          # every peer's stores into my rows have landed
+            self.hdl2[turn].barrier(channel=0)   # every peer's stores into my rows have landed
+            self.rows = self.rows2[turn]
             return self.rows
         dst = self.send if world > 1 else self.rows
         for s in range(world):

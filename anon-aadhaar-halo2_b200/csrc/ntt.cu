@@ -279,8 +279,9 @@ static void host_ntt(uint64_t* a, size_t stride, size_t count, uint32_t log_n, c
         io = (Fr*)c.scratch(s).ntt_io.get(count * n * sizeof(Fr));
     }
     Fr* tmp = (Fr*)c.scratch(s).ntt_tmp.get(count * n * sizeof(Fr));
-    if (count == 1 && !resident && log_n >= g_ntt_pipe_min_log_n && g_ntt_pipe_chunks > 1) {
-        // one large transform: upload column ranges under the first pass, download under the last
+    if (count == 1 && log_n >= g_ntt_pipe_min_log_n && g_ntt_pipe_chunks > 1) {
+        // one large transform: upload column ranges under the first pass (unless the polynomial is already
+        // resident in its mirror), download under the last
         constexpr int MAXC = NTT_PIPE_MAX_CHUNKS;
         cudaStream_t& up = g_ntt_up;
         cudaStream_t& down = g_ntt_down;
@@ -311,7 +312,7 @@ static void host_ntt(uint64_t* a, size_t stride, size_t count, uint32_t log_n, c
                 ZK_CUDA(cudaEventRecord(ev_start, s));              // earlier users of the staging buffers
                 ZK_CUDA(cudaStreamWaitEvent(up, ev_start, 0));
                 const uint64_t cols = ncols0 / (uint64_t)chunks;
-                for (int ch = 0; ch < chunks; ++ch) {
+                for (int ch = 0; ch < chunks && !resident; ++ch) {
                     ZK_CUDA(cudaMemcpy2DAsync(io + ch * cols, ncols0 * sizeof(Fr), (const Fr*)a + ch * cols, ncols0 * sizeof(Fr),
                                               cols * sizeof(Fr), rows0, cudaMemcpyHostToDevice, up));
                     ZK_CUDA(cudaEventRecord(ev_up[ch], up));
@@ -322,7 +323,9 @@ static void host_ntt(uint64_t* a, size_t stride, size_t count, uint32_t log_n, c
         if (uploaded) {
             NttChunkHooks hooks;
             hooks.chunks = chunks;
-            hooks.before_first = [&](int ch, uint64_t, uint64_t, uint64_t) { ZK_CUDA(cudaStreamWaitEvent(s, ev_up[ch], 0)); };
+            hooks.before_first = [&](int ch, uint64_t, uint64_t, uint64_t) {
+                if (!resident) ZK_CUDA(cudaStreamWaitEvent(s, ev_up[ch], 0));
+            };
             hooks.after_last = [&](int ch, uint64_t col0, uint64_t cols, uint64_t rows) {
                 const uint64_t ncols = n / rows;
                 ZK_CUDA(cudaEventRecord(ev_done[ch], s));
@@ -336,9 +339,15 @@ static void host_ntt(uint64_t* a, size_t stride, size_t count, uint32_t log_n, c
             return;
         }
     }
-    if (!resident)
-        ZK_CUDA(cudaMemcpy2DAsync(io, n * sizeof(Fr), a, stride * sizeof(Fr), n * sizeof(Fr), count,
-                                  cudaMemcpyHostToDevice, s));
+    if (count == 1) {           // plain copies: no 2-D descriptor on the prover's per-polynomial path
+        if (!resident) ZK_CUDA(cudaMemcpyAsync(io, a, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        ntt_run(c, io, n, io, n, tmp, 1, log_n, omega, mods, s);
+        ZK_CUDA(cudaMemcpyAsync(a, io, n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+        ZK_CUDA(cudaStreamSynchronize(s));
+        return;
+    }
+    ZK_CUDA(cudaMemcpy2DAsync(io, n * sizeof(Fr), a, stride * sizeof(Fr), n * sizeof(Fr), count,
+                              cudaMemcpyHostToDevice, s));
     ntt_run(c, io, n, io, n, tmp, count, log_n, omega, mods, s);
     ZK_CUDA(cudaMemcpy2DAsync(a, stride * sizeof(Fr), io, n * sizeof(Fr), n * sizeof(Fr), count,
                               cudaMemcpyDeviceToHost, s));

@@ -583,83 +583,7 @@ def main() -> None:
     # ---- e2e: the host-buffer C-ABI calls, pinned host memory, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        h_scal = torch.empty(n * 4, dtype=torch.int64, pin_memory=True)
-        h_ntt = torch.empty(n * 4, dtype=torch.int64, pin_memory=True)
-        h_scal.copy_(d_scal); h_ntt.copy_(d_scal)
-        torch.cuda.synchronize()
-        out = np.zeros(12, dtype=np.uint64)
-
-        def e2e_step():
-            b200zk.check(lib.b200zk_msm_g1_registered(handle.value, vp(h_scal), n, _ptr(out)))
-            if world > 1:
-                d_pt.copy_(torch.from_numpy(out.view(np.int64)))
-                dist.all_gather_into_tensor(gathered, d_pt)
-                if rank == 0:
-                    pts = gathered.cpu().numpy().view(np.uint64).reshape(world, 12)
-                    b200zk.g1_sum(np.ascontiguousarray(pts))
-            b200zk.check(lib.b200zk_ntt(vp(h_ntt), k, _ptr(omega)))
-
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": world * n * args.steps / dt / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": world * n * (32 + 32), "d2h_bytes_per_step": world * (n * 32 + 96),
-               "ms_per_step": 1e3 * dt / args.steps,
-               "api": "b200zk_msm_g1_registered (ParamsKZG::commit_lagrange: scalars from pinned host memory, "
-                      "SRS resident) + b200zk_ntt (best_fft in place on a pinned host buffer)"}
-        # the host-buffer calls (upload pipeline, transfer pipeline) against the device-resident ones on the
-        # same inputs: the commitment in canonical compressed form, the transform element for element
-        if rank == 0 and world == 1:
-            try:
-                dev_pt = d_pt.cpu().numpy().view(np.uint64).reshape(1, 12)
-                same_pt = bool(np.array_equal(b200zk.g1_to_bytes(np.ascontiguousarray(out.reshape(1, 12))),
-                                              b200zk.g1_to_bytes(np.ascontiguousarray(dev_pt))))
-                chk = torch.empty(n * 4, dtype=torch.int64, pin_memory=True)
-                chk.copy_(d_scal)
-                d_chk = d_scal.clone()
-                torch.cuda.synchronize()
-                b200zk.check(lib.b200zk_ntt(vp(chk), k, _ptr(omega)))
-                b200zk.check(lib.b200zk_ntt_dev(vp(d_chk), n, 1, k, _ptr(omega), None, None))
-                torch.cuda.synchronize()
-                same_ntt = bool(torch.equal(chk, d_chk.cpu()))
-                e2e["same_results_as_device_resident_calls"] = same_pt and same_ntt
-                del chk, d_chk
-            except Exception as ex:   # auxiliary: never take the headline line down
-                e2e["verify_error"] = str(ex)[:200]
-        # informational: the same two calls on a pageable numpy buffer (what a Rust Vec<Fr> is), and on
-        # that buffer after b200zk_host_register (what the shim does once per long-lived buffer)
-        if rank == 0 and world == 1:
-            try:
-                pg_scal = h_scal.numpy().view(np.uint64).reshape(n, 4).copy()
-                pg_ntt = pg_scal.copy()
-
-                def host_step():
-                    b200zk.check(lib.b200zk_msm_g1_registered(handle.value, _ptr(pg_scal), n, _ptr(out)))
-                    b200zk.check(lib.b200zk_ntt(_ptr(pg_ntt), k, _ptr(omega)))
-
-                def timed(reps=2):
-                    host_step()
-                    t0 = time.perf_counter()
-                    for _ in range(reps):
-                        host_step()
-                    return 1e3 * (time.perf_counter() - t0) / reps
-
-                e2e["pageable_ms_per_step"] = timed()
-                with b200zk.pinned(pg_scal), b200zk.pinned(pg_ntt):
-                    e2e["registered_ms_per_step"] = timed()
-                del pg_scal, pg_ntt
-            except Exception as ex:   # auxiliary: never take the headline line down
-                e2e["pageable_error"] = str(ex)[:200]
-        del h_scal, h_ntt
+        e2e = run_e2e(args, torch, dist, b200zk, lib, dev, world, rank, k, n, handle, d_scal, d_pt, gathered, omega, barrier)
 
     # ---- restated CPU baseline on this box's host cores (rank 0, N = 1)
     cpu_baseline = None
@@ -733,6 +657,173 @@ def main() -> None:
         dist.destroy_process_group()
 
 
+def run_e2e(args, torch, dist, b200zk, lib, dev, world, rank, k, n, handle, d_scal, d_pt, gathered, omega, barrier):
+    """The step through the host-pointer C ABI, page-locked host polynomials, every copy inside the timed region.
+
+    Headline (`value`): the prover's pattern — `commit_lagrange(p)` then a transform of the *same* polynomial p, as
+    create_proof does with every advice / lookup / permutation column (commit_lagrange, then lagrange_to_coeff).  With
+    the library's device mirrors on (b200zk_mirror_enable) the commit's upload is the only upload: the transform finds p
+    in HBM, runs there and writes the result back.  Every step starts from host data the library has not seen
+    (b200zk_mirror_invalidate: new witness values), so a step moves 2^k * 32 B up and 2^k * 32 B + 96 B down.
+    `separate_buffers`: round 1's definition (two unrelated host buffers, no mirrors: 2 * 2^k * 32 B up), kept for
+    comparison.  With N > 1 the odd ranks run one polynomial behind (transform of the previous polynomial, then the
+    commit of the next) so that half of the ranks upload while the other half downloads, and the one-point gather + fold
+    sits at the end of the step."""
+    from b200zk.api import _ptr
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    out = np.zeros(12, dtype=np.uint64)
+
+    def gather_fold():
+        if world > 1:
+            d_pt.copy_(torch.from_numpy(out.view(np.int64)))
+            dist.all_gather_into_tensor(gathered, d_pt)
+            if rank == 0:
+                pts = gathered.cpu().numpy().view(np.uint64).reshape(world, 12)
+                b200zk.g1_sum(np.ascontiguousarray(pts))
+
+    def timed(step_fn, steps, warm):
+        for _ in range(warm):
+            step_fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_fn()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- headline: one polynomial committed, then transformed (two buffers so that the odd ranks can lag by one)
+    polys = [torch.empty(n * 4, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    for p in polys:
+        p.copy_(d_scal)
+    torch.cuda.synchronize()
+    b200zk.check(lib.b200zk_mirror_enable(4 * n * 32))
+    state = {"i": 0}
+    lag = world > 1 and rank % 2 == 1
+
+    def shared_step():
+        cur, prev = polys[state["i"] & 1], polys[(state["i"] + 1) & 1]
+        state["i"] += 1
+        b200zk.check(lib.b200zk_mirror_invalidate(vp(cur), 0))       # new host data for this step's polynomial
+        if lag:
+            b200zk.check(lib.b200zk_ntt(vp(prev), k, _ptr(omega)))   # the polynomial committed one step ago
+            b200zk.check(lib.b200zk_msm_g1_registered(handle.value, vp(cur), n, _ptr(out)))
+        else:
+            b200zk.check(lib.b200zk_msm_g1_registered(handle.value, vp(cur), n, _ptr(out)))
+            b200zk.check(lib.b200zk_ntt(vp(cur), k, _ptr(omega)))
+        gather_fold()
+
+    dt = timed(shared_step, args.steps, max(2, min(args.warmup, 3)))
+    e2e = {"value": world * n * args.steps / dt / 1e6, "unit": UNIT,
+           "h2d_bytes_per_step": world * n * 32, "d2h_bytes_per_step": world * (n * 32 + 96),
+           "ms_per_step": 1e3 * dt / args.steps,
+           "api": "b200zk_msm_g1_registered (ParamsKZG::commit_lagrange: the polynomial from page-locked host memory, SRS "
+                  "resident) + b200zk_ntt (best_fft in place on the same host polynomial, found in its device mirror: "
+                  "b200zk_mirror_enable; b200zk_mirror_invalidate before every step: the host data is new)",
+           "rank_order": "odd ranks transform the previous polynomial before committing the next (half the ranks upload while "
+                         "half download)" if world > 1 else "commit, then transform"}
+    # same results as the device-resident calls on the same inputs (rank 0, single GPU)
+    if rank == 0 and world == 1:
+        try:
+            chk = polys[0]
+            chk.copy_(d_scal)
+            d_chk = d_scal.clone()
+            torch.cuda.synchronize()
+            b200zk.check(lib.b200zk_mirror_invalidate(vp(chk), 0))
+            b200zk.check(lib.b200zk_msm_g1_registered(handle.value, vp(chk), n, _ptr(out)))
+            b200zk.check(lib.b200zk_ntt(vp(chk), k, _ptr(omega)))
+            b200zk.check(lib.b200zk_msm_g1_registered_dev(handle.value, vp(d_scal), n, 1, n, vp(d_pt), None))
+            b200zk.check(lib.b200zk_ntt_dev(vp(d_chk), n, 1, k, _ptr(omega), None, None))
+            torch.cuda.synchronize()
+            dev_pt = d_pt.cpu().numpy().view(np.uint64).reshape(1, 12)
+            same_pt = bool(np.array_equal(b200zk.g1_to_bytes(np.ascontiguousarray(out.reshape(1, 12))),
+                                          b200zk.g1_to_bytes(np.ascontiguousarray(dev_pt))))
+            e2e["same_results_as_device_resident_calls"] = same_pt and bool(torch.equal(chk, d_chk.cpu()))
+            st = (C.c_uint64 * 4)()
+            b200zk.check(lib.b200zk_mirror_stats(st))
+            e2e["mirror_stats"] = {"hits": int(st[0]), "misses": int(st[1]), "resident_bytes": int(st[2])}
+            del d_chk
+        except Exception as ex:   # auxiliary: never take the headline line down
+            e2e["verify_error"] = str(ex)[:200]
+    b200zk.check(lib.b200zk_mirror_enable(0))
+
+    # ---- round 1's definition: two unrelated host buffers, no mirrors (1 GiB up + 0.5 GiB down at k = 24)
+    try:
+        h_scal, h_ntt = polys
+        h_scal.copy_(d_scal); h_ntt.copy_(d_scal)
+        torch.cuda.synchronize()
+
+        def separate_step():
+            b200zk.check(lib.b200zk_msm_g1_registered(handle.value, vp(h_scal), n, _ptr(out)))
+            gather_fold()
+            b200zk.check(lib.b200zk_ntt(vp(h_ntt), k, _ptr(omega)))
+
+        steps2 = max(2, min(args.steps, 5))
+        dt2 = timed(separate_step, steps2, 1)
+        e2e["separate_buffers"] = {"value": world * n * steps2 / dt2 / 1e6, "ms_per_step": 1e3 * dt2 / steps2, "steps": steps2,
+                                   "h2d_bytes_per_step": world * n * 64, "d2h_bytes_per_step": world * (n * 32 + 96),
+                                   "note": "round 1's e2e: the commit and the transform on two unrelated host buffers, no mirrors"}
+    except Exception as ex:
+        e2e["separate_buffers"] = {"error": str(ex)[:200]}
+
+    # ---- where the host side goes with N ranks: concurrent copy rates of all ranks (512 MiB each way)
+    if world > 1:
+        try:
+            nb = min(n * 32, 1 << 29)
+            hbuf, dbuf = polys[0][: nb // 8], torch.empty(nb // 8, dtype=torch.int64, device=dev)
+
+            def rate(fn):
+                fn(); torch.cuda.synchronize(); barrier()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                mine = 3 * nb / (time.perf_counter() - t0) / 1e9
+                t = torch.tensor([mine], dtype=torch.float64, device=dev)
+                lo, total = t.clone(), t.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(total, op=dist.ReduceOp.SUM)
+                return {"min_rank_GBps": float(lo.item()), "sum_GBps": float(total.item())}
+
+            up = lambda: dbuf.copy_(hbuf, non_blocking=True)
+            down = lambda: hbuf.copy_(dbuf, non_blocking=True)
+            e2e["pcie_concurrent"] = {"all_ranks_h2d": rate(up), "all_ranks_d2h": rate(down),
+                                      "even_h2d_odd_d2h": rate(up if rank % 2 == 0 else down),
+                                      "bytes_per_copy": nb}
+            del dbuf
+        except Exception as ex:
+            e2e["pcie_concurrent"] = {"error": str(ex)[:200]}
+
+    # informational: the round-1 step on a pageable numpy buffer (what a Rust Vec<Fr> is), and on that buffer after
+    # b200zk_host_register (what the shim does once per long-lived buffer)
+    if rank == 0 and world == 1:
+        try:
+            pg_scal = polys[0].numpy().view(np.uint64).reshape(n, 4).copy()
+            pg_ntt = pg_scal.copy()
+
+            def host_step():
+                b200zk.check(lib.b200zk_msm_g1_registered(handle.value, _ptr(pg_scal), n, _ptr(out)))
+                b200zk.check(lib.b200zk_ntt(_ptr(pg_ntt), k, _ptr(omega)))
+
+            def wall(reps=2):
+                host_step()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    host_step()
+                return 1e3 * (time.perf_counter() - t0) / reps
+
+            e2e["separate_buffers"]["pageable_ms_per_step"] = wall()
+            with b200zk.pinned(pg_scal), b200zk.pinned(pg_ntt):
+                e2e["separate_buffers"]["registered_ms_per_step"] = wall()
+            del pg_scal, pg_ntt
+        except Exception as ex:   # auxiliary: never take the headline line down
+            e2e["pageable_error"] = str(ex)[:200]
+    return e2e
+
+
 def run_sharded_ntt(torch, dist, lib, b200zk, world: int, rank: int, dev, k: int, single_ms: float):
     """One 2^k best_fft over all ranks (strong scaling of a single transform): local column
     NTTs, twiddle pass that stores straight into the peers' row buffers over NVLink (falls back
@@ -767,6 +858,7 @@ def run_sharded_ntt(torch, dist, lib, b200zk, world: int, rank: int, dev, k: int
 
 
 def run_proof_shape(torch, dist, world: int, rank: int, dev, cpu: bool):
+    import b200zk as b200zk_mod
     """The hot-path call sequence of one create_proof at the RSA-SHA256 circuit shape
     (k = 15, extended k = 17; SURVEY.md section 8 d) on synthetic columns, every rank one
     replica.  Returns per-stage milliseconds (median of 3 after one warm-up)."""
@@ -790,16 +882,38 @@ def run_proof_shape(torch, dist, world: int, rank: int, dev, cpu: bool):
         # ONE proof over all ranks: columns dealt for commit / iNTT, coefficient columns all-gathered,
         # every rank extends and evaluates its cosets of the extended domain, rank 0 finishes h(X)
         want = hp.h_coeff.to_host().copy()
+        want_pts = b200zk_mod.g1_to_bytes(np.ascontiguousarray(hp.points.to_host().reshape(-1, 12)))
         hp.prepare_sharded(world, rank)
+        dealt = [list(hp.commit_ranges)]
+        for _ in range(3):        # measure, re-deal the commitments by the measured load, repeat
+            hp.rebalance(torch, dist, hp.run_sharded(torch, dist))
+            dealt.append(list(hp.commit_ranges))
         hp.run_sharded(torch, dist)
-        same = bool(np.array_equal(hp.h_coeff.to_host(), want)) if rank == 0 else True
+        same = True
+        if rank == 0:
+            got_pts = b200zk_mod.g1_to_bytes(np.ascontiguousarray(hp.points.to_host().reshape(-1, 12)))
+            keep = list(range(hp.n_lag)) + [hp.n_lag + 1 + j for j in range(RSA_SHA256.degree - 1)]
+            same = bool(np.array_equal(hp.h_coeff.to_host(), want)) and bool(np.array_equal(got_pts[keep], want_pts[keep]))
         sruns = [hp.run_sharded(torch, dist) for _ in range(3)]
         smed = {k: statistics.median(r[k] for r in sruns) for k in sruns[0]}
         st = torch.tensor([smed["total"]], dtype=torch.float64, device=dev)
         dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        # the stage every rank spends longest in, and the slowest rank's share of it
+        names = [k for k in smed if k != "total"]
+        per_rank = torch.tensor([smed[k] for k in names], dtype=torch.float64, device=dev)
+        allr = torch.zeros(world * len(names), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, per_rank)
+        table = allr.view(world, len(names)).cpu().tolist()
+        worst = max(range(len(names)), key=lambda i: max(row[i] for row in table))
         sharded = {"one_proof_over_all_gpus_ms": float(st.item()), "speedup_vs_one_gpu": med["total"] / float(st.item()),
-                   "stages_ms_rank0": smed, "h_coefficients_equal_single_gpu": same,
-                   "exchange": "all-gather of coefficient columns (NCCL) + all-gather of evaluated h cosets"}
+                   "stages_ms_rank0": smed, "stages_ms_max_over_ranks": {nm: max(row[i] for row in table) for i, nm in enumerate(names)},
+                   "limiting_stage": names[worst],
+                   "commit_columns_per_rank": [e - b for b, e in hp.commit_ranges],
+                   "h_coefficients_and_commitments_equal_single_gpu": same,
+                   "schedule": "own share to coefficient form + all-gather; coset owners extend and evaluate their cosets; "
+                               "commitments dealt by measured load (coset owners and rank 0 commit fewer columns); the evaluated "
+                               "cosets travel to rank 0 asynchronously; rank 0 finishes h(X)",
+                   "exchange": "all-gather of coefficient columns (NCCL) + asynchronous all-gather of evaluated h cosets + all-gather of commitments"}
     # ---- the same proof through the ABI the Rust patch binds under an *untouched* create_proof: one synchronous
     # host-pointer call per polynomial (page-locked host polynomials), without and with device mirrors
     percall = None
@@ -817,7 +931,6 @@ def run_proof_shape(torch, dist, world: int, rank: int, dev, cpu: bool):
                 np.array_equal(b200zk_mod.g1_to_bytes(np.ascontiguousarray(hp.h_points)), b200zk_mod.g1_to_bytes(np.ascontiguousarray(want_pts))))
             return {k: statistics.median(r[k] for r in runs) for k in runs[0]}, same
 
-        import b200zk as b200zk_mod
         plain, same_plain = leg(False)
         mirrored, same_mirrored = leg(True)
         percall = {"what": "one synchronous host-pointer C-ABI call per polynomial, as rust/halo2_proofs_patch binds them under an "
