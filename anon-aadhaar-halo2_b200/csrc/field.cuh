@@ -122,6 +122,139 @@ ZK_HD void mad_row4_stray(uint32_t& lo, uint32_t stray, uint32_t* acc, uint32_t 
 
 ZK_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 
+// acc(2N limbs) += sum_{t<N} x[2t] * y * 2^(64 t); the carry out of limb 2N-1 is added to acc[2N], which the
+// callers arrange to hold nothing but earlier such carries (see sqr()).  x is read with stride 2.
+template <int N> ZK_HD void mad_chain(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#ifdef __CUDA_ARCH__
+    if constexpr (N == 1) {
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32 %2, %2, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(x[0]), "r"(y));
+    } else if constexpr (N == 2) {
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32 %4, %4, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(x[0]), "r"(x[2]), "r"(y));
+    } else if constexpr (N == 3) {
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+            "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+            "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+            "addc.u32 %6, %6, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+            : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(y));
+    } else {
+        asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+              "+r"(acc[7]), "+r"(acc[8])
+            : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
+    }
+#else
+    uint64_t carry = 0;
+    for (int t = 0; t < N; ++t) {
+        unsigned __int128 s = (unsigned __int128)x[2 * t] * y + (((uint64_t)acc[2 * t + 1] << 32) | acc[2 * t]) + carry;
+        acc[2 * t] = (uint32_t)s;
+        acc[2 * t + 1] = (uint32_t)(s >> 32);
+        carry = (uint64_t)(s >> 64);
+    }
+    acc[2 * N] += (uint32_t)carry;
+#endif
+}
+
+// r(16 limbs) = a + b (16 limbs each); no carry leaves limb 15 for the operands sqr() forms
+ZK_HD void add16(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %16, %32;\n\t"
+        "addc.cc.u32 %1, %17, %33;\n\t"
+        "addc.cc.u32 %2, %18, %34;\n\t"
+        "addc.cc.u32 %3, %19, %35;\n\t"
+        "addc.cc.u32 %4, %20, %36;\n\t"
+        "addc.cc.u32 %5, %21, %37;\n\t"
+        "addc.cc.u32 %6, %22, %38;\n\t"
+        "addc.cc.u32 %7, %23, %39;\n\t"
+        "addc.cc.u32 %8, %24, %40;\n\t"
+        "addc.cc.u32 %9, %25, %41;\n\t"
+        "addc.cc.u32 %10, %26, %42;\n\t"
+        "addc.cc.u32 %11, %27, %43;\n\t"
+        "addc.cc.u32 %12, %28, %44;\n\t"
+        "addc.cc.u32 %13, %29, %45;\n\t"
+        "addc.cc.u32 %14, %30, %46;\n\t"
+        "addc.u32 %15, %31, %47;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]),
+          "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]), "r"(b[0]), "r"(b[1]), "r"(b[2]),
+          "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]), "r"(b[11]),
+          "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 16; ++i) {
+        uint64_t s = (uint64_t)a[i] + b[i] + c;
+        r[i] = (uint32_t)s;
+        c = s >> 32;
+    }
+#endif
+}
+
+// lo += stray, returning the carry (0 / 1) of that addition
+ZK_HD uint32_t add_carry_out(uint32_t& lo, uint32_t stray) {
+#ifdef __CUDA_ARCH__
+    uint32_t c;
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "addc.u32 %1, 0, 0;"
+        : "+r"(lo), "=r"(c) : "r"(stray));
+    return c;
+#else
+    uint64_t s = (uint64_t)lo + stray;
+    lo = (uint32_t)s;
+    return (uint32_t)(s >> 32);
+#endif
+}
+
+// acc(8 limbs) += sum_t x[t] * y * 2^(64 t) + cin (cin = 0 / 1 enters at limb 0); no carry leaves limb 7
+ZK_HD void mad_row4_cin(uint32_t* acc, uint32_t cin, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t"
+        ".reg .u32 t;\n\t"
+        "add.cc.u32 t, %8, 0xffffffff;\n\t"          // carry flag = cin
+        "madc.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.u32 %7, %12, %13, %7;\n\t"
+        "}"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7])
+        : "r"(cin), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+#else
+    const uint32_t x[4] = {x0, x1, x2, x3};
+    uint64_t carry = cin;
+    for (int t = 0; t < 4; ++t) {
+        unsigned __int128 s = (unsigned __int128)x[t] * y + (((uint64_t)acc[2 * t + 1] << 32) | acc[2 * t]) + carry;
+        acc[2 * t] = (uint32_t)s;
+        acc[2 * t + 1] = (uint32_t)(s >> 32);
+        carry = (uint64_t)(s >> 64);
+    }
+#endif
+}
+
+
 // r = a + b (8 limbs), returns carry
 ZK_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #ifdef __CUDA_ARCH__
@@ -317,7 +450,91 @@ struct alignas(16) Fp {
         add8(r.l, E, s);
         return r;
     }
-    ZK_HD Fp sqr() const { return (*this) * (*this); }
+    // Montgomery square a*a*2^-256 mod p, the same representative operator* returns (the reduction multiplier
+    // M = -T p^-1 mod 2^256 depends on T = a^2 only), with 36 + 64 + 8 multiplier-pipe operations instead of
+    // 64 + 64 + 8:
+    //   1. the 28 cross products a_i a_j (i < j) once, in two 16-limb accumulators like operator*'s: a product
+    //      at limb position i + j goes to E (even positions) or to O (odd positions, O[k] = limb k + 1), so every
+    //      chain is aligned multiply-adds; rows are ordered so that a chain's final carry lands in a limb that
+    //      holds only earlier carries;
+    //   2. T = 2 (E + 2^32 O) + sum_i a_i^2 2^(64 i)   (shifts and adds: the other pipe);
+    //   3. Q = (T mod R + M p) / R by eight reduction rows (operator*'s rows without the a b_i terms), and the
+    //      result Q + floor(T / R) < 2p.
+    ZK_HD Fp sqr() const {
+#ifdef B200ZK_SQR_BY_MUL           // A/B builds only (build.py --variant)
+        return (*this) * (*this);
+#endif
+        uint32_t E[17], O[17];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) { E[i] = 0; O[i] = 0; }
+        const uint32_t* a = l;
+        // odd positions i + j: O index i + j - 1
+        mad_chain<4>(O + 0, a + 1, a[0]);     // a0 * (a1, a3, a5, a7) -> limbs 0..7, carry -> 8
+        mad_chain<3>(O + 2, a + 2, a[1]);     // a1 * (a2, a4, a6)     -> 2..7,  carry -> 8
+        mad_chain<3>(O + 4, a + 3, a[2]);     // a2 * (a3, a5, a7)     -> 4..9,  carry -> 10
+        mad_chain<2>(O + 6, a + 4, a[3]);     // a3 * (a4, a6)         -> 6..9,  carry -> 10
+        mad_chain<2>(O + 8, a + 5, a[4]);     // a4 * (a5, a7)         -> 8..11, carry -> 12
+        mad_chain<1>(O + 10, a + 6, a[5]);    // a5 * a6               -> 10,11, carry -> 12
+        mad_chain<1>(O + 12, a + 7, a[6]);    // a6 * a7               -> 12,13, carry -> 14
+        // even positions i + j: E index i + j
+        mad_chain<3>(E + 2, a + 2, a[0]);     // a0 * (a2, a4, a6)     -> 2..7,  carry -> 8
+        mad_chain<3>(E + 4, a + 3, a[1]);     // a1 * (a3, a5, a7)     -> 4..9,  carry -> 10
+        mad_chain<2>(E + 6, a + 4, a[2]);     // a2 * (a4, a6)         -> 6..9,  carry -> 10
+        mad_chain<2>(E + 8, a + 5, a[3]);     // a3 * (a5, a7)         -> 8..11, carry -> 12
+        mad_chain<1>(E + 10, a + 6, a[4]);    // a4 * a6               -> 10,11, carry -> 12
+        mad_chain<1>(E + 12, a + 7, a[5]);    // a5 * a7               -> 12,13, carry -> 14
+        // X = E + 2^32 O  (sum of the cross products, < 2^509)
+        uint32_t S[16], X[16], T[16], D[16];
+        S[0] = 0;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) S[i] = O[i - 1];
+        add16(X, E, S);
+        // 2 X, and the diagonal a_i^2 at limbs 2i, 2i + 1
+        S[0] = X[0] << 1;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) S[i] = (X[i] << 1) | (X[i - 1] >> 31);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint64_t d = (uint64_t)a[i] * a[i];
+            D[2 * i] = (uint32_t)d;
+            D[2 * i + 1] = (uint32_t)(d >> 32);
+        }
+        add16(T, S, D);
+        // Montgomery reduction of the low half
+        uint32_t m[8];
+        modulus(m);
+        uint32_t stray = 0;
+        uint32_t RE[9], RO[9];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { RE[i] = T[i]; RO[i] = 0; }
+        RE[8] = 0; RO[8] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t c0 = add_carry_out(RE[0], stray);
+            const uint32_t mi = mul_lo(RE[0], P::INV);
+            RE[8] += mad_row4(RE, m[0], m[2], m[4], m[6], mi);
+            mad_row4_cin(RO, c0, m[1], m[3], m[5], m[7], mi);
+            stray = RE[1];
+            uint32_t nO[9];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) nO[j] = RE[j + 2];
+            nO[7] = 0; nO[8] = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) RE[j] = RO[j];
+            RE[8] = 0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) RO[j] = nO[j];
+        }
+        // Q = RE + stray + 2^32 RO (<= p), result = Q + T[8..15] (< 2p)
+        Fp q, r;
+        uint32_t sh[8];
+        sh[0] = stray;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) sh[j] = RO[j - 1];
+        add8(q.l, RE, sh);
+        add8(r.l, q.l, T + 8);
+        return r;
+    }
 
     // canonical integer -> Montgomery, and back
     ZK_HD Fp to_mont() const { return (*this) * r2(); }

@@ -855,6 +855,7 @@ struct MsmPre {
 static bool g_msm_quad = getenv("B200ZK_MSM_QUAD") ? atoi(getenv("B200ZK_MSM_QUAD")) != 0 : true;
 static uint32_t g_msm_finish_max = getenv("B200ZK_MSM_FINISH_MAX") ? (uint32_t)atoi(getenv("B200ZK_MSM_FINISH_MAX")) : 48u;
 static size_t g_msm_quad_reduce_max = getenv("B200ZK_MSM_QUAD_REDUCE_MAX") ? (size_t)atoll(getenv("B200ZK_MSM_QUAD_REDUCE_MAX")) : ((size_t)1 << 14);
+static uint32_t g_msm_finish_max_keys = getenv("B200ZK_MSM_FINISH_MAX_KEYS") ? (uint32_t)atoi(getenv("B200ZK_MSM_FINISH_MAX_KEYS")) : (1u << 18);
 static uint32_t g_msm_finish_max_threads = getenv("B200ZK_MSM_FINISH_MAX_THREADS") ? (uint32_t)atoi(getenv("B200ZK_MSM_FINISH_MAX_THREADS")) : (1u << 19);
 static uint32_t g_msm_quad_max = getenv("B200ZK_MSM_QUAD_MAX") ? (uint32_t)atoi(getenv("B200ZK_MSM_QUAD_MAX")) : (1u << 17);
 
@@ -1069,9 +1070,10 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
                                                                        buckets, keyA, ptA);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_COMBINE);
-    if (g_msm_quad && nthreads0 <= g_msm_finish_max_threads) {
+    if (g_msm_quad && nthreads0 <= g_msm_finish_max_threads && nkeys <= g_msm_finish_max_keys) {
         // latency regime (a single small commit): every bucket's open partials by one quad; the keyed levels below
-        // only run when a bucket was too long for it.  (At 2^24 the levels are cheaper: 0.64 ms against 1.56 ms.)
+        // only run when a bucket was too long for it.  (With 2^21 buckets — a 2^24 commit, or one point range of its
+        // upload pipeline — the levels are cheaper: 0.64 ms against 1.56 ms.)
         msm_finish_quad_kernel<<<(nkeys * 4u + 127u) / 128u, 128, 0, s>>>(start, nkeys, run, g_msm_finish_max, buckets, ptA);
         ZK_LAUNCH_CHECK();
         run_combine_levels(c, keyA, ptA, keyB, ptB, nthreads0, run->level_count, buckets, s, &run->any_long);

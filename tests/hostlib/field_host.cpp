@@ -18,6 +18,8 @@ void h_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { st(r, ld<Fq>(
 void h_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { st(r, ld<Fq>(a) - ld<Fq>(b)); }
 void h_fq_neg(const uint32_t* a, uint32_t* r) { st(r, ld<Fq>(a).neg()); }
 void h_fq_inv(const uint32_t* a, uint32_t* r) { st(r, ld<Fq>(a).inverse()); }
+void h_fr_sqr_raw(const uint32_t* a, uint32_t* r) { st_raw(r, ld<Fr>(a).sqr()); }
+void h_fq_sqr_raw(const uint32_t* a, uint32_t* r) { st_raw(r, ld<Fq>(a).sqr()); }
 void h_fr_mul_raw(const uint32_t* a, const uint32_t* b, uint32_t* r) { st_raw(r, ld<Fr>(a) * ld<Fr>(b)); }
 void h_fq_mul_raw(const uint32_t* a, const uint32_t* b, uint32_t* r) { st_raw(r, ld<Fq>(a) * ld<Fq>(b)); }
 void h_fr_add_raw(const uint32_t* a, const uint32_t* b, uint32_t* r) { st_raw(r, ld<Fr>(a) + ld<Fr>(b)); }
