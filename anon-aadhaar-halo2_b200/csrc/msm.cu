@@ -783,6 +783,7 @@ static void msm_release_pipeline() {          // b200zk_shutdown: the next init 
     g_msm_copy_stream = nullptr;
 }
 static void msm_release_stage_events();
+static uint32_t g_msm_chunk_div_small = getenv("B200ZK_MSM_CHUNK_DIV_SMALL") ? (uint32_t)atoi(getenv("B200ZK_MSM_CHUNK_DIV_SMALL")) : 512u;
 static uint32_t g_msm_chunk_div = getenv("B200ZK_MSM_CHUNK_DIV") ? (uint32_t)atoi(getenv("B200ZK_MSM_CHUNK_DIV")) : 2048u;
 static uint32_t g_msm_force_sub = getenv("B200ZK_MSM_SUB_BITS") ? (uint32_t)atoi(getenv("B200ZK_MSM_SUB_BITS")) : 0xffffffffu;
 // stage events are kept per stream (a profiled MSM on one stream does not disturb another's);
@@ -838,6 +839,10 @@ static uint32_t choose_window(size_t n, bool shared_buckets) {
         const double cost = 10.0 * (double)n * W + 30.0 * (shared_buckets ? 1.0 : W) * (double)(1u << (c - 1));
         if (cost < best) { best = cost; bc = c; }
     }
+    // up to 2^18 points one commit is latency-bound: 2^15 buckets keep the bucket reduction in its 4-lane
+    // cooperative form (<= 2^14 segments), worth more than the 1/16 fewer additions of one more bit
+    // (2^17 points: 1.01 ms at c = 17, 0.89 ms at c = 16)
+    if (shared_buckets && n <= ((size_t)1 << 18) && bc > 16) bc = 16;
     return bc;
 }
 
@@ -1024,7 +1029,10 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     // chunks mean fewer open runs handed to the keyed-reduction levels; measured on B200 against
     // 4096 / 1024 / 512: 1.79 -> 1.59 ms at 2^18, 4.27 -> 3.99 ms at 2^20, unchanged from 2^23 up).
     // Chosen by the device from the pair count it has just produced (MsmRun).
-    const uint32_t chunk_unit = (uint32_t)c.sm_count * g_msm_chunk_div;
+    // A single small commit (latency regime, finished directly by quads) prefers ~4x longer chunks: half as many
+    // open partials per bucket for the finish (2^15 points: 0.441 -> 0.416 ms per commit at 512 against 2048).
+    const bool small_regime = g_msm_quad && max_pairs <= ((size_t)1 << 22) && nkeys <= g_msm_finish_max_keys;
+    const uint32_t chunk_unit = (uint32_t)c.sm_count * (small_regime ? std::min<uint32_t>(g_msm_chunk_div, g_msm_chunk_div_small) : g_msm_chunk_div);
     scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(start, cursor, bsum, nkeys, total, chunk_unit, g_msm_max_chunk, run);
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SCATTER);
