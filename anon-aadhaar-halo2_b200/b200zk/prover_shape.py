@@ -494,25 +494,9 @@ class ProverHotPath:
         self._deal_commits()
 
     def _deal_commits(self) -> None:
-        """Column counts x_r with fixed_r + column_r * x_r equal for all ranks (water filling), sum = n_lag."""
-        world, total = self.world, self.n_lag
-        col, fixed = self.cost["column"], self.cost["fixed"]
-        lo, hi = min(fixed), max(fixed) + max(col) * total
-        for _ in range(60):                                  # the finish time t at which sum_r max(0, (t - fixed_r) / col_r) = total
-            t = 0.5 * (lo + hi)
-            if sum(max(0.0, (t - fixed[r]) / col[r]) for r in range(world)) >= total:
-                hi = t
-            else:
-                lo = t
-        want = [max(0.0, (hi - fixed[r]) / col[r]) for r in range(world)]
-        counts = [int(w) for w in want]
-        for r in sorted(range(world), key=lambda r: want[r] - counts[r], reverse=True)[: total - sum(counts)]:
-            counts[r] += 1
-        self.commit_ranges, b = [], 0
-        for r in range(world):
-            self.commit_ranges.append((b, b + counts[r]))
-            b += counts[r]
-        assert b == total
+        """Column counts x_r with fixed_r + column_r * x_r equal for all ranks (sharding.deal_by_load)."""
+        from .sharding import deal_by_load
+        self.commit_ranges = deal_by_load(self.n_lag, self.cost["column"], self.cost["fixed"])
 
     def rebalance(self, torch, dist, t: dict) -> None:
         """Replace the cost model by the last run's measurements (all ranks) and deal the commitments again."""

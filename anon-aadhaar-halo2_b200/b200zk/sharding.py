@@ -29,6 +29,40 @@ def assign_columns(n_columns: int, rank: int, world: int) -> list:
     return list(range(rank, n_columns, world))
 
 
+def deal_by_load(total: int, per_item: list, fixed: list) -> list:
+    """Contiguous [begin, end) ranges of `total` items, one per rank, such that fixed[r] + per_item[r] * count_r is
+    as equal as integers allow (water filling): a rank with other work (cosets of h(X), the finish on rank 0) gets
+    fewer columns to commit.  Ranks whose fixed cost exceeds the common finish time get none."""
+    world = len(fixed)
+    assert world == len(per_item) and world >= 1 and all(c > 0 for c in per_item)
+    lo, hi = min(fixed), max(fixed) + max(per_item) * max(total, 1)
+    for _ in range(64):                # the finish time t with sum_r max(0, (t - fixed_r) / per_item_r) = total
+        t = 0.5 * (lo + hi)
+        if sum(max(0.0, (t - fixed[r]) / per_item[r]) for r in range(world)) >= total:
+            hi = t
+        else:
+            lo = t
+    want = [max(0.0, (hi - fixed[r]) / per_item[r]) for r in range(world)]
+    counts = [min(int(w), total) for w in want]
+    short = total - sum(counts)
+    order = sorted(range(world), key=lambda r: want[r] - counts[r], reverse=True)
+    i = 0
+    while short > 0:                   # hand the rounding remainder to the largest fractional parts
+        counts[order[i % world]] += 1
+        short -= 1
+        i += 1
+    while short < 0:
+        r = max(range(world), key=lambda r: counts[r])
+        counts[r] -= 1
+        short += 1
+    ranges, b = [], 0
+    for r in range(world):
+        ranges.append((b, b + counts[r]))
+        b += counts[r]
+    assert b == total
+    return ranges
+
+
 def _dist():
     import torch.distributed as dist
     return dist

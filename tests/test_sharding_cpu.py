@@ -122,3 +122,37 @@ def test_two_rank_gloo_msm_split_and_h_gather():
         assert p.exitcode == 0
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] and r[2] for r in results), results
+
+
+def test_deal_by_load_equalises_finish_times():
+    """The commitments of a sharded proof are dealt by load (b200zk/sharding.py deal_by_load): every item is dealt
+    exactly once, in contiguous ranges, and fixed + per_item * count is level across ranks up to one item."""
+    import random
+
+    from b200zk.sharding import deal_by_load
+
+    # the 8-GPU proof of DESIGN.md section 7: four coset owners (rank 0 also finishes h(X)), four plain ranks
+    ranges = deal_by_load(242, [0.135] * 8, [3.4 + 1.05, 3.4, 3.4, 3.4, 0.0, 0.0, 0.0, 0.0])
+    counts = [e - b for b, e in ranges]
+    assert sum(counts) == 242 and ranges[0][0] == 0 and all(ranges[i][1] == ranges[i + 1][0] for i in range(7))
+    assert counts[0] < min(counts[1:4]) and max(counts[1:4]) < min(counts[4:])
+    assert max(counts[1:4]) - min(counts[1:4]) <= 1 and max(counts[4:]) - min(counts[4:]) <= 1
+    fin = [f + 0.135 * c for f, c in zip([4.45, 3.4, 3.4, 3.4, 0, 0, 0, 0], counts)]
+    assert max(fin) - min(fin) <= 0.135 + 1e-9
+    # a rank whose other work exceeds everybody's finish time gets nothing; a single rank gets everything
+    assert [e - b for b, e in deal_by_load(10, [1.0, 1.0], [100.0, 0.0])] == [0, 10]
+    assert deal_by_load(7, [0.3], [5.0]) == [(0, 7)] and deal_by_load(0, [1.0, 2.0], [0.0, 0.0]) == [(0, 0), (0, 0)]
+    rnd = random.Random(3)
+    for _ in range(200):
+        world = rnd.randint(1, 8)
+        per = [rnd.uniform(0.05, 0.4) for _ in range(world)]
+        fixed = [rnd.uniform(0.0, 6.0) for _ in range(world)]
+        total = rnd.randint(0, 400)
+        rg = deal_by_load(total, per, fixed)
+        cnt = [e - b for b, e in rg]
+        assert sum(cnt) == total and all(c >= 0 for c in cnt)
+        busy = [r for r in range(world) if cnt[r] > 0]
+        if busy:
+            fin = [fixed[r] + per[r] * cnt[r] for r in busy]
+            assert max(fin) - min(fin) <= 2 * max(per) + 1e-9
+            assert all(fixed[r] >= min(fin) - 2 * max(per) for r in range(world) if cnt[r] == 0)
