@@ -308,6 +308,281 @@ __global__ void msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n,
     sorted[pos] = ((uint32_t)i + index_offset + w * table_stride) | (d < 0 ? 0x80000000u : 0u);
 }
 
+// ------------------------------------------------ 1'-3'. two-level partition sort (large MSMs)
+// The counting sort above bumps one L2 counter per pair twice (201 M `RED` + 201 M `ATOM` at 2^24: 1.6 + 5.5 ms,
+// the second with a 4-byte store at a random place of a 805 MB list).  For large inputs the pairs are sorted in two
+// levels instead, with every per-pair counter in shared memory:
+//   A. keys are split into <= 4096 partitions by their high bits; a block ranks a tile of 8192 digits by partition in
+//      shared memory, reserves room for each partition with one global atomic per (tile, partition) and writes
+//      8-byte records (point | sign, low key bits) into the partition's region;
+//   B. inside a partition (<= 2048 buckets) a block ranks a tile of records by bucket in shared memory — first only
+//      counting, for the exact bucket offsets the accumulation needs, then again to place the 4-byte entries, one
+//      global atomic per (tile, bucket).
+// Global atomics drop from 2 per pair to ~0.4, the random 4-byte stores become runs, and the bucket offsets
+// (`start`), the sorted list and the device plan come out exactly as from the counting sort.
+constexpr uint32_t PSORT_TILE = 8192;        // entries per block (256 threads x 32)
+constexpr uint32_t PSORT_THREADS = 256;
+constexpr uint32_t PSORT_MAX_PARTS = 4096;
+constexpr uint32_t PSORT_MAX_SHIFT = 12;     // <= 4096 buckets per partition
+
+struct PsortArgs {
+    uint32_t c, nwin, key_windows, shift, nparts;
+    uint32_t table_stride, index_offset;
+};
+
+__device__ __forceinline__ bool psort_decode(const PsortArgs& A, int32_t d, uint32_t cw, uint32_t& key) {
+    if (d == 0) return false;
+    const uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+    const uint32_t col = cw / A.nwin, w = cw - col * A.nwin;
+    const uint32_t group = col * A.key_windows + (A.key_windows > 1 ? w : 0);
+    key = (group << (A.c - 1)) + mag - 1;
+    return true;
+}
+
+// digits (as msm_hist_kernel) + the number of pairs of every partition
+__global__ void __launch_bounds__(256) msm_digits_count_kernel(const Fr* __restrict__ scalars, size_t scalar_stride, size_t n,
+                                                               PsortArgs A, uint32_t* __restrict__ part_count,
+                                                               int32_t* __restrict__ digits) {
+    __shared__ uint32_t sh[PSORT_MAX_PARTS];
+    for (uint32_t t = threadIdx.x; t < A.nparts; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+    const uint32_t col = blockIdx.y;
+    const uint32_t c = A.c, nwin = A.nwin;
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1u;
+#pragma unroll 1
+    for (uint32_t j = 0; j < 8; ++j) {
+        const size_t i = ((size_t)blockIdx.x * 8 + j) * blockDim.x + threadIdx.x;
+        if (i >= n) break;
+        const Fr s = ldg_fr(scalars + (size_t)col * scalar_stride + i).from_mont();
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < nwin; ++w) {
+            const uint32_t o = w * c;
+            const uint32_t limb = o >> 5, shb = o & 31u;
+            uint32_t raw = 0;
+            if (limb < 8) {
+                raw = s.l[limb] >> shb;
+                if (shb + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - shb);
+            }
+            const uint32_t d = (raw & mask) + carry;
+            int32_t sd;
+            if (d > half) { sd = (int32_t)d - (int32_t)(1u << c); carry = 1; }
+            else { sd = (int32_t)d; carry = 0; }
+            digits[((size_t)col * nwin + w) * n + i] = sd;
+            uint32_t key;
+            if (psort_decode(A, sd, col * nwin + w, key)) atomicAdd(&sh[key >> A.shift], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < A.nparts; t += blockDim.x)
+        if (sh[t]) atomicAdd(part_count + t, sh[t]);
+}
+
+// exclusive scans of the partition sizes (-> part_start, a copy as cursors) and of their tile counts (-> tile_prefix)
+__global__ void __launch_bounds__(1024) msm_partition_scan_kernel(const uint32_t* __restrict__ part_count, uint32_t nparts,
+                                                                  uint32_t* __restrict__ part_start, uint32_t* __restrict__ part_cursor,
+                                                                  uint32_t* __restrict__ tile_prefix) {
+    __shared__ uint32_t sa[PSORT_MAX_PARTS + 1], sb[PSORT_MAX_PARTS + 1];
+    for (uint32_t t = threadIdx.x; t < nparts; t += blockDim.x) {
+        const uint32_t v = part_count[t];
+        sa[t] = v;
+        sb[t] = (v + PSORT_TILE - 1) / PSORT_TILE;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {                   // two serial scans of <= 4096 entries, side by side
+        uint32_t* a = threadIdx.x == 0 ? sa : sb;
+        uint32_t run = 0;
+        for (uint32_t t = 0; t < nparts; ++t) { const uint32_t v = a[t]; a[t] = run; run += v; }
+        a[nparts] = run;
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t <= nparts; t += blockDim.x) {
+        part_start[t] = sa[t];
+        if (t < nparts) part_cursor[t] = sa[t];
+        tile_prefix[t] = sb[t];
+    }
+}
+
+// Block-wide exclusive scan of cnt[0..nbins) in place (nbins <= 4096, 256 threads: up to 16 consecutive bins each),
+// then one global reservation per non-empty bin: delta[bin] = (position reserved in `cursor`) - (local position),
+// so that the element at local sorted position q of bin `bin` goes to global position delta[bin] + q.
+// `rot` rotates which bins a thread reserves, so that concurrent blocks do not hit the same counters in step.
+// Returns the number of elements of the tile.  tot: 257 words of shared memory.
+__device__ __forceinline__ uint32_t psort_scan_reserve(uint32_t* cnt, uint32_t* delta, uint32_t nbins, uint32_t* cursor,
+                                                       uint32_t rot, uint32_t* tot) {
+    const uint32_t per = (nbins + PSORT_THREADS - 1) / PSORT_THREADS;      // <= 16
+    const uint32_t t = (threadIdx.x + rot) % PSORT_THREADS;                 // logical slot of this thread
+    const uint32_t b0 = t * per;
+    uint32_t local[16];
+    uint32_t sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) {
+        local[j] = (j < per && b0 + j < nbins) ? cnt[b0 + j] : 0u;
+        sum += local[j];
+    }
+    tot[t] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {                // one warp scans the 256 slot sums, 8 each
+        uint32_t v[8], s8 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j] = tot[threadIdx.x * 8 + j]; s8 += v[j]; }
+        uint32_t x = s8;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (threadIdx.x >= (uint32_t)o) x += y;
+        }
+        if (threadIdx.x == 31) tot[PSORT_THREADS] = x;
+        uint32_t run = x - s8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { tot[threadIdx.x * 8 + j] = run; run += v[j]; }
+    }
+    __syncthreads();
+    uint32_t run = tot[t];
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) {
+        if (j < per && b0 + j < nbins) {
+            cnt[b0 + j] = run;                                             // local exclusive offset
+            delta[b0 + j] = local[j] ? atomicAdd(cursor + b0 + j, local[j]) - run : 0u;
+            run += local[j];
+        }
+    }
+    __syncthreads();
+    return tot[PSORT_THREADS];
+}
+
+// A: digits -> records grouped by partition.  The tile is ordered by partition in shared memory first, so that
+// consecutive threads store consecutive records of a partition's run: a scattered 8-byte store per lane is a memory
+// request each, and 201 M of them were most of the first version's 4.1 ms.
+__global__ void __launch_bounds__(PSORT_THREADS, 2) msm_partition_scatter_kernel(const int32_t* __restrict__ digits, size_t n,
+                                                                                 uint64_t total, PsortArgs A,
+                                                                                 uint32_t* __restrict__ part_cursor,
+                                                                                 uint2* __restrict__ rec) {
+    extern __shared__ uint4 psort_smem[];
+    uint2* sh_rec = reinterpret_cast<uint2*>(psort_smem);                  // PSORT_TILE records
+    uint32_t* sh_cnt = reinterpret_cast<uint32_t*>(sh_rec + PSORT_TILE);   // PSORT_MAX_PARTS
+    uint32_t* sh_delta = sh_cnt + PSORT_MAX_PARTS;                         // PSORT_MAX_PARTS
+    uint32_t* sh_tot = sh_delta + PSORT_MAX_PARTS;                         // 257
+    for (uint32_t t = threadIdx.x; t < A.nparts; t += blockDim.x) sh_cnt[t] = 0;
+    __syncthreads();
+    constexpr int PER = PSORT_TILE / PSORT_THREADS;
+    uint32_t pr[PER], val[PER], kl[PER];
+    const uint64_t base = (uint64_t)blockIdx.x * PSORT_TILE;
+    // (column, window) row and position of the tile's first entry; entries advance without divisions
+    const uint32_t cw0 = (uint32_t)(base / n);
+    const uint64_t i0 = base - (uint64_t)cw0 * n;
+    const uint32_t lowmask = (1u << A.shift) - 1u;
+    // all loads first: a shared-memory atomic between two loads keeps the compiler from overlapping them, and 32
+    // dependent round trips to DRAM per thread were 60 % of this kernel's stall samples
+    int32_t dv[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const uint64_t e = base + (uint64_t)j * PSORT_THREADS + threadIdx.x;
+        dv[j] = e < total ? __ldcs(digits + e) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        uint64_t i = i0 + (uint64_t)j * PSORT_THREADS + threadIdx.x;
+        uint32_t cw = cw0;
+        while (i >= n) { i -= n; ++cw; }
+        const int32_t d = dv[j];
+        pr[j] = 0xffffffffu;
+        uint32_t key;
+        if (psort_decode(A, d, cw, key)) {
+            const uint32_t p = key >> A.shift;
+            const uint32_t w = cw % A.nwin;
+            val[j] = ((uint32_t)i + A.index_offset + w * A.table_stride) | (d < 0 ? 0x80000000u : 0u);
+            kl[j] = (key & lowmask) | (p << 16);
+            pr[j] = (p << 16) | atomicAdd(&sh_cnt[p], 1u);
+        }
+    }
+    __syncthreads();
+    const uint32_t pop = psort_scan_reserve(sh_cnt, sh_delta, A.nparts, part_cursor, blockIdx.x * 7u, sh_tot);
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (pr[j] != 0xffffffffu) sh_rec[sh_cnt[pr[j] >> 16] + (pr[j] & 0xffffu)] = make_uint2(val[j], kl[j]);
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < pop; q += PSORT_THREADS) {
+        const uint2 r = sh_rec[q];
+        rec[sh_delta[r.y >> 16] + q] = make_uint2(r.x, r.y & 0xffffu);
+    }
+}
+
+// the partition and record range of a block of pass B
+__device__ __forceinline__ bool psort_tile(const uint32_t* __restrict__ tile_prefix, const uint32_t* __restrict__ part_start,
+                                           uint32_t nparts, uint32_t& p, uint32_t& lo, uint32_t& hi) {
+    const uint32_t b = blockIdx.x;
+    if (b >= __ldg(tile_prefix + nparts)) return false;
+    uint32_t l = 0, h = nparts;                       // tile_prefix[l] <= b < tile_prefix[h]
+    while (h - l > 1) {
+        const uint32_t m = (l + h) >> 1;
+        if (__ldg(tile_prefix + m) <= b) l = m; else h = m;
+    }
+    p = l;
+    lo = __ldg(part_start + p) + (b - __ldg(tile_prefix + p)) * PSORT_TILE;
+    hi = min(lo + PSORT_TILE, __ldg(part_start + p + 1));
+    return true;
+}
+
+// B1: exact size of every bucket
+__global__ void __launch_bounds__(PSORT_THREADS) msm_bucket_count_kernel(const uint2* __restrict__ rec, PsortArgs A,
+                                                                         const uint32_t* __restrict__ tile_prefix,
+                                                                         const uint32_t* __restrict__ part_start,
+                                                                         uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[1u << PSORT_MAX_SHIFT];
+    uint32_t p, lo, hi;
+    if (!psort_tile(tile_prefix, part_start, A.nparts, p, lo, hi)) return;
+    const uint32_t nbins = 1u << A.shift;
+    for (uint32_t t = threadIdx.x; t < nbins; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+    for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) atomicAdd(&sh[__ldg(&rec[e].y)], 1u);
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < nbins; t += blockDim.x)
+        if (sh[t]) atomicAdd(hist + ((size_t)p << A.shift) + t, sh[t]);
+}
+
+// B2: records -> the sorted list of (point | sign) entries, ordered by bucket in shared memory first (see A)
+__global__ void __launch_bounds__(PSORT_THREADS, 2) msm_bucket_scatter_kernel(const uint2* __restrict__ rec, PsortArgs A,
+                                                                              const uint32_t* __restrict__ tile_prefix,
+                                                                              const uint32_t* __restrict__ part_start,
+                                                                              uint32_t* __restrict__ cursor,
+                                                                              uint32_t* __restrict__ sorted) {
+    extern __shared__ uint4 psort_smem[];
+    uint2* sh_rec = reinterpret_cast<uint2*>(psort_smem);                  // PSORT_TILE x (value, bucket)
+    uint32_t* sh_cnt = reinterpret_cast<uint32_t*>(sh_rec + PSORT_TILE);   // 2^PSORT_MAX_SHIFT
+    uint32_t* sh_delta = sh_cnt + (1u << PSORT_MAX_SHIFT);
+    uint32_t* sh_tot = sh_delta + (1u << PSORT_MAX_SHIFT);
+    uint32_t p, lo, hi;
+    if (!psort_tile(tile_prefix, part_start, A.nparts, p, lo, hi)) return;
+    const uint32_t nbins = 1u << A.shift;
+    for (uint32_t t = threadIdx.x; t < nbins; t += blockDim.x) sh_cnt[t] = 0;
+    __syncthreads();
+    constexpr int PER = PSORT_TILE / PSORT_THREADS;
+    uint32_t val[PER], kr[PER];
+    uint32_t kb[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {          // all loads first (see msm_partition_scatter_kernel)
+        const uint32_t e = lo + (uint32_t)j * PSORT_THREADS + threadIdx.x;
+        const uint2 r = e < hi ? __ldcs(rec + e) : make_uint2(0u, 0xffffffffu);
+        val[j] = r.x;
+        kb[j] = r.y;
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        kr[j] = 0xffffffffu;
+        if (kb[j] != 0xffffffffu) kr[j] = (kb[j] << 16) | atomicAdd(&sh_cnt[kb[j]], 1u);
+    }
+    __syncthreads();
+    const uint32_t pop = psort_scan_reserve(sh_cnt, sh_delta, nbins, cursor + ((size_t)p << A.shift), blockIdx.x * 7u, sh_tot);
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (kr[j] != 0xffffffffu) sh_rec[sh_cnt[kr[j] >> 16] + (kr[j] & 0xffffu)] = make_uint2(val[j], kr[j] >> 16);
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < pop; q += PSORT_THREADS) {
+        const uint2 r = sh_rec[q];
+        sorted[sh_delta[r.y] + q] = r.x;
+    }
+}
+
 constexpr uint32_t MSM_PAD_KEY = 0xffffffffu;   // padding lane (real keys are < 2^31)
 
 // ------------------------------------------------------- 4. bucket accumulation, level 0
@@ -864,6 +1139,9 @@ struct MsmPre {
 static bool g_msm_quad = getenv("B200ZK_MSM_QUAD") ? atoi(getenv("B200ZK_MSM_QUAD")) != 0 : true;
 static uint32_t g_msm_finish_max = getenv("B200ZK_MSM_FINISH_MAX") ? (uint32_t)atoi(getenv("B200ZK_MSM_FINISH_MAX")) : 48u;
 static size_t g_msm_quad_reduce_max = getenv("B200ZK_MSM_QUAD_REDUCE_MAX") ? (size_t)atoll(getenv("B200ZK_MSM_QUAD_REDUCE_MAX")) : ((size_t)1 << 14);
+static bool g_msm_psort = getenv("B200ZK_MSM_PSORT") ? atoi(getenv("B200ZK_MSM_PSORT")) != 0 : true;
+static uint32_t g_msm_psort_shift = getenv("B200ZK_MSM_PSORT_SHIFT") ? std::min<uint32_t>((uint32_t)atoi(getenv("B200ZK_MSM_PSORT_SHIFT")), PSORT_MAX_SHIFT) : 11u;
+static size_t g_msm_psort_min_pairs = getenv("B200ZK_MSM_PSORT_MIN_PAIRS") ? (size_t)atoll(getenv("B200ZK_MSM_PSORT_MIN_PAIRS")) : ((size_t)1 << 22);
 static uint32_t g_msm_finish_max_keys = getenv("B200ZK_MSM_FINISH_MAX_KEYS") ? (uint32_t)atoi(getenv("B200ZK_MSM_FINISH_MAX_KEYS")) : (1u << 18);
 static uint32_t g_msm_finish_max_threads = getenv("B200ZK_MSM_FINISH_MAX_THREADS") ? (uint32_t)atoi(getenv("B200ZK_MSM_FINISH_MAX_THREADS")) : (1u << 19);
 static uint32_t g_msm_quad_max = getenv("B200ZK_MSM_QUAD_MAX") ? (uint32_t)atoi(getenv("B200ZK_MSM_QUAD_MAX")) : (1u << 17);
@@ -1000,6 +1278,10 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     const size_t o_run = carve(sizeof(MsmRun));
     const size_t o_sorted = carve(max_pairs * 4);
     const size_t o_digits = carve(max_pairs * 4);
+    // two-level partition sort (large inputs): 8-byte records + the partition tables
+    const bool psort = g_msm_psort && max_pairs >= g_msm_psort_min_pairs && nkeys <= ((size_t)PSORT_MAX_PARTS << PSORT_MAX_SHIFT);
+    const size_t o_rec = carve(psort ? max_pairs * 8 : 0);
+    const size_t o_ptab = carve(psort ? (size_t)(4 * (PSORT_MAX_PARTS + 1)) * 4 : 0);
     char* base = (char*)c.scratch(s).msm_work.get(off);
     uint32_t* hist = (uint32_t*)(base + o_hist);
     uint32_t* start = (uint32_t*)(base + o_start);
@@ -1021,9 +1303,45 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     }
     const unsigned sblocks = (unsigned)((n + 255) / 256);
     T.mark(MSM_ST_HIST);
-    msm_hist_kernel<<<dim3(sblocks, (unsigned)count), 256, 0, s>>>(d_scalars, scalar_stride, n, cbits, nwin,
-                                                                    key_windows, hist, digits);
-    ZK_LAUNCH_CHECK();
+    PsortArgs PA{};
+    uint32_t* ptab = (uint32_t*)(base + o_ptab);
+    uint32_t* part_count = ptab, *part_start = ptab + (PSORT_MAX_PARTS + 1), *part_cursor = ptab + 2 * (PSORT_MAX_PARTS + 1),
+            *tile_prefix = ptab + 3 * (PSORT_MAX_PARTS + 1);
+    uint2* rec = (uint2*)(base + o_rec);
+    const unsigned ptiles = (unsigned)((max_pairs + PSORT_TILE - 1) / PSORT_TILE);
+    if (psort) {
+        PA.c = cbits; PA.nwin = nwin; PA.key_windows = key_windows;
+        // as few partitions as the per-partition bucket count (<= 2^11) allows: the partition cursors are the one
+        // set of counters every tile of pass A contends for (2^21 keys: 1024 partitions of 2048 buckets)
+        PA.shift = g_msm_psort_shift;
+        while (PA.shift > 0 && ((size_t)1 << PA.shift) > (size_t)nkeys) --PA.shift;
+        while ((((size_t)nkeys + ((size_t)1 << PA.shift) - 1) >> PA.shift) > PSORT_MAX_PARTS) ++PA.shift;
+        PA.nparts = (uint32_t)(((size_t)nkeys + ((size_t)1 << PA.shift) - 1) >> PA.shift);
+        PA.table_stride = pre ? (uint32_t)pre->n_reg : 0u;
+        PA.index_offset = part.index_offset;
+        ZK_CUDA(cudaMemsetAsync(part_count, 0, (PSORT_MAX_PARTS + 1) * 4, s));
+        msm_digits_count_kernel<<<dim3((unsigned)((n + 2047) / 2048), (unsigned)count), 256, 0, s>>>(d_scalars, scalar_stride, n, PA,
+                                                                                                       part_count, digits);
+        ZK_LAUNCH_CHECK();
+        msm_partition_scan_kernel<<<1, 1024, 0, s>>>(part_count, PA.nparts, part_start, part_cursor, tile_prefix);
+        ZK_LAUNCH_CHECK();
+        constexpr int smemA = PSORT_TILE * 8 + 2 * PSORT_MAX_PARTS * 4 + 260 * 4;
+        constexpr int smemB = PSORT_TILE * 8 + 2 * (1 << PSORT_MAX_SHIFT) * 4 + 260 * 4;
+        static int psort_configured_device = -1;
+        if (psort_configured_device != c.device) {
+            ZK_CUDA(cudaFuncSetAttribute(msm_partition_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemA));
+            ZK_CUDA(cudaFuncSetAttribute(msm_bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB));
+            psort_configured_device = c.device;
+        }
+        msm_partition_scatter_kernel<<<ptiles, PSORT_THREADS, smemA, s>>>(digits, n, (uint64_t)max_pairs, PA, part_cursor, rec);
+        ZK_LAUNCH_CHECK();
+        msm_bucket_count_kernel<<<ptiles + PA.nparts, PSORT_THREADS, 0, s>>>(rec, PA, tile_prefix, part_start, hist);
+        ZK_LAUNCH_CHECK();
+    } else {
+        msm_hist_kernel<<<dim3(sblocks, (unsigned)count), 256, 0, s>>>(d_scalars, scalar_stride, n, cbits, nwin,
+                                                                        key_windows, hist, digits);
+        ZK_LAUNCH_CHECK();
+    }
     T.mark(MSM_ST_SCAN);
     scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, s>>>(hist, start, bsum, nkeys);
     ZK_LAUNCH_CHECK();
@@ -1044,8 +1362,13 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     // layout (6.4 -> 5.5 ms) and none helps the per-window layout
     uint32_t sub_bits = (pre && n * 4 > ((size_t)16 << 20) && cbits > 2 && count * nwin * 2 <= 65535) ? 1u : 0u;
     if (g_msm_force_sub != 0xffffffffu) sub_bits = std::min<uint32_t>(g_msm_force_sub, cbits - 1);
-    msm_scatter_kernel<<<dim3(sblocks, (unsigned)((count * nwin) << sub_bits)), 256, 0, s>>>(
-        digits, n, cbits, nwin, key_windows, pre ? (uint32_t)pre->n_reg : 0u, sub_bits, part.index_offset, cursor, sorted);
+    if (psort) {
+        msm_bucket_scatter_kernel<<<ptiles + PA.nparts, PSORT_THREADS, PSORT_TILE * 8 + 2 * (1 << PSORT_MAX_SHIFT) * 4 + 260 * 4, s>>>(
+            rec, PA, tile_prefix, part_start, cursor, sorted);
+    } else {
+        msm_scatter_kernel<<<dim3(sblocks, (unsigned)((count * nwin) << sub_bits)), 256, 0, s>>>(
+            digits, n, cbits, nwin, key_windows, pre ? (uint32_t)pre->n_reg : 0u, sub_bits, part.index_offset, cursor, sorted);
+    }
     ZK_LAUNCH_CHECK();
     T.mark(MSM_ST_SYNC);
     // No host round trip for the pair count: the accumulation is launched for the largest thread count any

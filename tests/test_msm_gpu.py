@@ -298,3 +298,46 @@ def test_sparse_scalars_plan_on_the_device(zk, kind):
         assert jac_affine(params.commit_lagrange(sc)) == exp
     finally:
         params.close()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "all_equal", "all_r_minus_1", "zero_one", "sparse"])
+def test_partition_sort_sizes_with_skewed_scalars(zk, kind):
+    """2^19 points is past the size from which the (bucket, point) pairs are sorted in two levels through shared
+    memory (csrc/msm.cu, partition sort).  Scalars that put every point of a window into one bucket, or almost none
+    anywhere, are the far ends of its tile-local counters; both the window-table commit and the plain best_multiexp
+    are checked against [sum s_i t_i] G with exact integers."""
+    import torch
+
+    lib = zk.load()
+    k = 19
+    n = 1 << k
+    db = torch.empty(n * 8, dtype=torch.int64, device="cuda")
+    zk.check(lib.b200zk_gen_points_dev(C.c_void_p(db.data_ptr()), n, 0xBA5E0000 + k, 0))
+    s = co.gen_scalars(0xA11CE000 + k, n)
+    if kind == "all_equal":
+        s[:] = s[7]
+    elif kind == "all_r_minus_1":
+        s[:] = bn.fr_array_from_canonical([bn.R - 1])[0]
+    elif kind == "zero_one":
+        s[:] = bn.fr_array_from_canonical([1])[0]
+        s[::2] = 0
+    elif kind == "sparse":
+        s[np.arange(n) % 10 != 0] = 0
+    ds = torch.from_numpy(s.view(np.int64).reshape(-1)).cuda()
+    torch.cuda.synchronize()
+    with np.errstate(over="ignore"):
+        t = bn._splitmix64_np(np.uint64(((0xBA5E0000 + k) << 32) & ((1 << 64) - 1)) + np.arange(n, dtype=np.uint64)) | np.uint64(1)
+    want = bn.g1_mul(bn.G1_GEN, _dot_mod_r(s, t) % bn.R * pow(1 << 256, -1, bn.R) % bn.R)
+    plain = np.zeros(12, dtype=np.uint64)
+    zk.check(lib.b200zk_msm_g1_dev(C.c_void_p(ds.data_ptr()), C.c_void_p(db.data_ptr()), n, C.c_void_p(plain.ctypes.data), None))
+    assert jac_affine(plain) == want
+    hb = db.cpu().numpy().view(np.uint64).reshape(n, 8)
+    h = C.c_uint64(0)
+    zk.check(lib.b200zk_bases_register(C.c_void_p(hb.ctypes.data), n, C.byref(h)))
+    try:
+        d_out = torch.zeros(12, dtype=torch.int64, device="cuda")
+        zk.check(lib.b200zk_msm_g1_registered_dev(h.value, C.c_void_p(ds.data_ptr()), n, 1, n, C.c_void_p(d_out.data_ptr()), None))
+        torch.cuda.synchronize()
+        assert jac_affine(d_out.cpu().numpy().view(np.uint64)) == want
+    finally:
+        zk.check(lib.b200zk_bases_evict(h.value))
