@@ -320,8 +320,11 @@ __global__ void msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n,
 //      global atomic per (tile, bucket).
 // Global atomics drop from 2 per pair to ~0.4, the random 4-byte stores become runs, and the bucket offsets
 // (`start`), the sorted list and the device plan come out exactly as from the counting sort.
-constexpr uint32_t PSORT_TILE = 8192;        // entries per block (256 threads x 32)
-constexpr uint32_t PSORT_THREADS = 256;
+// tiles of 32 entries per thread.  Measured at 2^24 (scratch A/B builds): pass A is fastest with 8192-entry tiles
+// (256 threads, two blocks per SM), pass B with 16384-entry tiles (512 threads: runs of 8 entries per bucket instead
+// of 4 in the ordered write-out): 1.49 -> 1.19 ms for B2, while the same tile made A 0.2 ms slower.
+constexpr uint32_t PSORT_THREADS_A = 256, PSORT_TILE_A = 32 * PSORT_THREADS_A;
+constexpr uint32_t PSORT_THREADS_B = 512, PSORT_TILE_B = 32 * PSORT_THREADS_B;
 constexpr uint32_t PSORT_MAX_PARTS = 4096;
 constexpr uint32_t PSORT_MAX_SHIFT = 12;     // <= 4096 buckets per partition
 
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(1024) msm_partition_scan_kernel(const uint32_t
     for (uint32_t t = threadIdx.x; t < nparts; t += blockDim.x) {
         const uint32_t v = part_count[t];
         sa[t] = v;
-        sb[t] = (v + PSORT_TILE - 1) / PSORT_TILE;
+        sb[t] = (v + PSORT_TILE_B - 1) / PSORT_TILE_B;
     }
     __syncthreads();
     if (threadIdx.x < 2) {                   // two serial scans of <= 4096 entries, side by side
@@ -407,9 +410,11 @@ __global__ void __launch_bounds__(1024) msm_partition_scan_kernel(const uint32_t
 // so that the element at local sorted position q of bin `bin` goes to global position delta[bin] + q.
 // `rot` rotates which bins a thread reserves, so that concurrent blocks do not hit the same counters in step.
 // Returns the number of elements of the tile.  tot: 257 words of shared memory.
+template <uint32_t THREADS>
 __device__ __forceinline__ uint32_t psort_scan_reserve(uint32_t* cnt, uint32_t* delta, uint32_t nbins, uint32_t* cursor,
                                                        uint32_t rot, uint32_t* tot) {
-    const uint32_t per = (nbins + PSORT_THREADS - 1) / PSORT_THREADS;      // <= 16
+    constexpr uint32_t PSORT_THREADS = THREADS;
+    const uint32_t per = (nbins + PSORT_THREADS - 1) / PSORT_THREADS;      // <= 16 (4096 bins / 256 threads)
     const uint32_t t = (threadIdx.x + rot) % PSORT_THREADS;                 // logical slot of this thread
     const uint32_t b0 = t * per;
     uint32_t local[16];
@@ -421,10 +426,11 @@ __device__ __forceinline__ uint32_t psort_scan_reserve(uint32_t* cnt, uint32_t* 
     }
     tot[t] = sum;
     __syncthreads();
-    if (threadIdx.x < 32) {                // one warp scans the 256 slot sums, 8 each
-        uint32_t v[8], s8 = 0;
+    constexpr int SLOTS = PSORT_THREADS / 32;
+    if (threadIdx.x < 32) {                // one warp scans the slot sums, SLOTS each
+        uint32_t v[SLOTS], s8 = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { v[j] = tot[threadIdx.x * 8 + j]; s8 += v[j]; }
+        for (int j = 0; j < SLOTS; ++j) { v[j] = tot[threadIdx.x * SLOTS + j]; s8 += v[j]; }
         uint32_t x = s8;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -434,7 +440,7 @@ __device__ __forceinline__ uint32_t psort_scan_reserve(uint32_t* cnt, uint32_t* 
         if (threadIdx.x == 31) tot[PSORT_THREADS] = x;
         uint32_t run = x - s8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { tot[threadIdx.x * 8 + j] = run; run += v[j]; }
+        for (int j = 0; j < SLOTS; ++j) { tot[threadIdx.x * SLOTS + j] = run; run += v[j]; }
     }
     __syncthreads();
     uint32_t run = tot[t];
@@ -453,20 +459,20 @@ __device__ __forceinline__ uint32_t psort_scan_reserve(uint32_t* cnt, uint32_t* 
 // A: digits -> records grouped by partition.  The tile is ordered by partition in shared memory first, so that
 // consecutive threads store consecutive records of a partition's run: a scattered 8-byte store per lane is a memory
 // request each, and 201 M of them were most of the first version's 4.1 ms.
-__global__ void __launch_bounds__(PSORT_THREADS, 2) msm_partition_scatter_kernel(const int32_t* __restrict__ digits, size_t n,
+__global__ void __launch_bounds__(PSORT_THREADS_A, 2) msm_partition_scatter_kernel(const int32_t* __restrict__ digits, size_t n,
                                                                                  uint64_t total, PsortArgs A,
                                                                                  uint32_t* __restrict__ part_cursor,
                                                                                  uint2* __restrict__ rec) {
     extern __shared__ uint4 psort_smem[];
-    uint2* sh_rec = reinterpret_cast<uint2*>(psort_smem);                  // PSORT_TILE records
-    uint32_t* sh_cnt = reinterpret_cast<uint32_t*>(sh_rec + PSORT_TILE);   // PSORT_MAX_PARTS
+    uint2* sh_rec = reinterpret_cast<uint2*>(psort_smem);                  // PSORT_TILE_A records
+    uint32_t* sh_cnt = reinterpret_cast<uint32_t*>(sh_rec + PSORT_TILE_A);   // PSORT_MAX_PARTS
     uint32_t* sh_delta = sh_cnt + PSORT_MAX_PARTS;                         // PSORT_MAX_PARTS
-    uint32_t* sh_tot = sh_delta + PSORT_MAX_PARTS;                         // 257
+    uint32_t* sh_tot = sh_delta + PSORT_MAX_PARTS;                         // PSORT_THREADS_A + 1
     for (uint32_t t = threadIdx.x; t < A.nparts; t += blockDim.x) sh_cnt[t] = 0;
     __syncthreads();
-    constexpr int PER = PSORT_TILE / PSORT_THREADS;
+    constexpr int PER = PSORT_TILE_A / PSORT_THREADS_A;
     uint32_t pr[PER], val[PER], kl[PER];
-    const uint64_t base = (uint64_t)blockIdx.x * PSORT_TILE;
+    const uint64_t base = (uint64_t)blockIdx.x * PSORT_TILE_A;
     // (column, window) row and position of the tile's first entry; entries advance without divisions
     const uint32_t cw0 = (uint32_t)(base / n);
     const uint64_t i0 = base - (uint64_t)cw0 * n;
@@ -476,12 +482,12 @@ __global__ void __launch_bounds__(PSORT_THREADS, 2) msm_partition_scatter_kernel
     int32_t dv[PER];
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-        const uint64_t e = base + (uint64_t)j * PSORT_THREADS + threadIdx.x;
+        const uint64_t e = base + (uint64_t)j * PSORT_THREADS_A + threadIdx.x;
         dv[j] = e < total ? __ldcs(digits + e) : 0;
     }
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-        uint64_t i = i0 + (uint64_t)j * PSORT_THREADS + threadIdx.x;
+        uint64_t i = i0 + (uint64_t)j * PSORT_THREADS_A + threadIdx.x;
         uint32_t cw = cw0;
         while (i >= n) { i -= n; ++cw; }
         const int32_t d = dv[j];
@@ -496,12 +502,12 @@ __global__ void __launch_bounds__(PSORT_THREADS, 2) msm_partition_scatter_kernel
         }
     }
     __syncthreads();
-    const uint32_t pop = psort_scan_reserve(sh_cnt, sh_delta, A.nparts, part_cursor, blockIdx.x * 7u, sh_tot);
+    const uint32_t pop = psort_scan_reserve<PSORT_THREADS_A>(sh_cnt, sh_delta, A.nparts, part_cursor, blockIdx.x * 7u, sh_tot);
 #pragma unroll
     for (int j = 0; j < PER; ++j)
         if (pr[j] != 0xffffffffu) sh_rec[sh_cnt[pr[j] >> 16] + (pr[j] & 0xffffu)] = make_uint2(val[j], kl[j]);
     __syncthreads();
-    for (uint32_t q = threadIdx.x; q < pop; q += PSORT_THREADS) {
+    for (uint32_t q = threadIdx.x; q < pop; q += PSORT_THREADS_A) {
         const uint2 r = sh_rec[q];
         rec[sh_delta[r.y >> 16] + q] = make_uint2(r.x, r.y & 0xffffu);
     }
@@ -518,13 +524,13 @@ __device__ __forceinline__ bool psort_tile(const uint32_t* __restrict__ tile_pre
         if (__ldg(tile_prefix + m) <= b) l = m; else h = m;
     }
     p = l;
-    lo = __ldg(part_start + p) + (b - __ldg(tile_prefix + p)) * PSORT_TILE;
-    hi = min(lo + PSORT_TILE, __ldg(part_start + p + 1));
+    lo = __ldg(part_start + p) + (b - __ldg(tile_prefix + p)) * PSORT_TILE_B;
+    hi = min(lo + PSORT_TILE_B, __ldg(part_start + p + 1));
     return true;
 }
 
 // B1: exact size of every bucket
-__global__ void __launch_bounds__(PSORT_THREADS) msm_bucket_count_kernel(const uint2* __restrict__ rec, PsortArgs A,
+__global__ void __launch_bounds__(PSORT_THREADS_B) msm_bucket_count_kernel(const uint2* __restrict__ rec, PsortArgs A,
                                                                          const uint32_t* __restrict__ tile_prefix,
                                                                          const uint32_t* __restrict__ part_start,
                                                                          uint32_t* __restrict__ hist) {
@@ -541,14 +547,14 @@ __global__ void __launch_bounds__(PSORT_THREADS) msm_bucket_count_kernel(const u
 }
 
 // B2: records -> the sorted list of (point | sign) entries, ordered by bucket in shared memory first (see A)
-__global__ void __launch_bounds__(PSORT_THREADS, 2) msm_bucket_scatter_kernel(const uint2* __restrict__ rec, PsortArgs A,
+__global__ void __launch_bounds__(PSORT_THREADS_B, 1) msm_bucket_scatter_kernel(const uint2* __restrict__ rec, PsortArgs A,
                                                                               const uint32_t* __restrict__ tile_prefix,
                                                                               const uint32_t* __restrict__ part_start,
                                                                               uint32_t* __restrict__ cursor,
                                                                               uint32_t* __restrict__ sorted) {
     extern __shared__ uint4 psort_smem[];
-    uint2* sh_rec = reinterpret_cast<uint2*>(psort_smem);                  // PSORT_TILE x (value, bucket)
-    uint32_t* sh_cnt = reinterpret_cast<uint32_t*>(sh_rec + PSORT_TILE);   // 2^PSORT_MAX_SHIFT
+    uint2* sh_rec = reinterpret_cast<uint2*>(psort_smem);                  // PSORT_TILE_B x (value, bucket)
+    uint32_t* sh_cnt = reinterpret_cast<uint32_t*>(sh_rec + PSORT_TILE_B);   // 2^PSORT_MAX_SHIFT
     uint32_t* sh_delta = sh_cnt + (1u << PSORT_MAX_SHIFT);
     uint32_t* sh_tot = sh_delta + (1u << PSORT_MAX_SHIFT);
     uint32_t p, lo, hi;
@@ -556,12 +562,12 @@ __global__ void __launch_bounds__(PSORT_THREADS, 2) msm_bucket_scatter_kernel(co
     const uint32_t nbins = 1u << A.shift;
     for (uint32_t t = threadIdx.x; t < nbins; t += blockDim.x) sh_cnt[t] = 0;
     __syncthreads();
-    constexpr int PER = PSORT_TILE / PSORT_THREADS;
+    constexpr int PER = PSORT_TILE_B / PSORT_THREADS_B;
     uint32_t val[PER], kr[PER];
     uint32_t kb[PER];
 #pragma unroll
     for (int j = 0; j < PER; ++j) {          // all loads first (see msm_partition_scatter_kernel)
-        const uint32_t e = lo + (uint32_t)j * PSORT_THREADS + threadIdx.x;
+        const uint32_t e = lo + (uint32_t)j * PSORT_THREADS_B + threadIdx.x;
         const uint2 r = e < hi ? __ldcs(rec + e) : make_uint2(0u, 0xffffffffu);
         val[j] = r.x;
         kb[j] = r.y;
@@ -572,12 +578,12 @@ __global__ void __launch_bounds__(PSORT_THREADS, 2) msm_bucket_scatter_kernel(co
         if (kb[j] != 0xffffffffu) kr[j] = (kb[j] << 16) | atomicAdd(&sh_cnt[kb[j]], 1u);
     }
     __syncthreads();
-    const uint32_t pop = psort_scan_reserve(sh_cnt, sh_delta, nbins, cursor + ((size_t)p << A.shift), blockIdx.x * 7u, sh_tot);
+    const uint32_t pop = psort_scan_reserve<PSORT_THREADS_B>(sh_cnt, sh_delta, nbins, cursor + ((size_t)p << A.shift), blockIdx.x * 7u, sh_tot);
 #pragma unroll
     for (int j = 0; j < PER; ++j)
         if (kr[j] != 0xffffffffu) sh_rec[sh_cnt[kr[j] >> 16] + (kr[j] & 0xffffu)] = make_uint2(val[j], kr[j] >> 16);
     __syncthreads();
-    for (uint32_t q = threadIdx.x; q < pop; q += PSORT_THREADS) {
+    for (uint32_t q = threadIdx.x; q < pop; q += PSORT_THREADS_B) {
         const uint2 r = sh_rec[q];
         sorted[sh_delta[r.y] + q] = r.x;
     }
@@ -1308,7 +1314,8 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     uint32_t* part_count = ptab, *part_start = ptab + (PSORT_MAX_PARTS + 1), *part_cursor = ptab + 2 * (PSORT_MAX_PARTS + 1),
             *tile_prefix = ptab + 3 * (PSORT_MAX_PARTS + 1);
     uint2* rec = (uint2*)(base + o_rec);
-    const unsigned ptiles = (unsigned)((max_pairs + PSORT_TILE - 1) / PSORT_TILE);
+    const unsigned ptiles_a = (unsigned)((max_pairs + PSORT_TILE_A - 1) / PSORT_TILE_A);
+    const unsigned ptiles_b = (unsigned)((max_pairs + PSORT_TILE_B - 1) / PSORT_TILE_B);
     if (psort) {
         PA.c = cbits; PA.nwin = nwin; PA.key_windows = key_windows;
         // as few partitions as the per-partition bucket count (<= 2^11) allows: the partition cursors are the one
@@ -1325,17 +1332,17 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
         ZK_LAUNCH_CHECK();
         msm_partition_scan_kernel<<<1, 1024, 0, s>>>(part_count, PA.nparts, part_start, part_cursor, tile_prefix);
         ZK_LAUNCH_CHECK();
-        constexpr int smemA = PSORT_TILE * 8 + 2 * PSORT_MAX_PARTS * 4 + 260 * 4;
-        constexpr int smemB = PSORT_TILE * 8 + 2 * (1 << PSORT_MAX_SHIFT) * 4 + 260 * 4;
+        constexpr int smemA = PSORT_TILE_A * 8 + 2 * PSORT_MAX_PARTS * 4 + (PSORT_THREADS_A + 4) * 4;
+        constexpr int smemB = PSORT_TILE_B * 8 + 2 * (1 << PSORT_MAX_SHIFT) * 4 + (PSORT_THREADS_B + 4) * 4;
         static int psort_configured_device = -1;
         if (psort_configured_device != c.device) {
             ZK_CUDA(cudaFuncSetAttribute(msm_partition_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemA));
             ZK_CUDA(cudaFuncSetAttribute(msm_bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB));
             psort_configured_device = c.device;
         }
-        msm_partition_scatter_kernel<<<ptiles, PSORT_THREADS, smemA, s>>>(digits, n, (uint64_t)max_pairs, PA, part_cursor, rec);
+        msm_partition_scatter_kernel<<<ptiles_a, PSORT_THREADS_A, smemA, s>>>(digits, n, (uint64_t)max_pairs, PA, part_cursor, rec);
         ZK_LAUNCH_CHECK();
-        msm_bucket_count_kernel<<<ptiles + PA.nparts, PSORT_THREADS, 0, s>>>(rec, PA, tile_prefix, part_start, hist);
+        msm_bucket_count_kernel<<<ptiles_b + PA.nparts, PSORT_THREADS_B, 0, s>>>(rec, PA, tile_prefix, part_start, hist);
         ZK_LAUNCH_CHECK();
     } else {
         msm_hist_kernel<<<dim3(sblocks, (unsigned)count), 256, 0, s>>>(d_scalars, scalar_stride, n, cbits, nwin,
@@ -1363,7 +1370,7 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     uint32_t sub_bits = (pre && n * 4 > ((size_t)16 << 20) && cbits > 2 && count * nwin * 2 <= 65535) ? 1u : 0u;
     if (g_msm_force_sub != 0xffffffffu) sub_bits = std::min<uint32_t>(g_msm_force_sub, cbits - 1);
     if (psort) {
-        msm_bucket_scatter_kernel<<<ptiles + PA.nparts, PSORT_THREADS, PSORT_TILE * 8 + 2 * (1 << PSORT_MAX_SHIFT) * 4 + 260 * 4, s>>>(
+        msm_bucket_scatter_kernel<<<ptiles_b + PA.nparts, PSORT_THREADS_B, PSORT_TILE_B * 8 + 2 * (1 << PSORT_MAX_SHIFT) * 4 + (PSORT_THREADS_B + 4) * 4, s>>>(
             rec, PA, tile_prefix, part_start, cursor, sorted);
     } else {
         msm_scatter_kernel<<<dim3(sblocks, (unsigned)((count * nwin) << sub_bits)), 256, 0, s>>>(
