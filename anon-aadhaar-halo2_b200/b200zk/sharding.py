@@ -129,13 +129,22 @@ def gather_extended_chunks(local_chunk: np.ndarray, size: int, device=None) -> n
 # natural order, which is what makes one all-to-all enough (the host-side scatter / gather of
 # a natural-order vector is a strided copy, `column_block` / `natural_from_row_blocks`).
 
+NTT_MAX_PASS_BITS = 9      # csrc/ntt.cuh NTT_MAX_B: one pass of the transform kernel covers at most 2^9 points
+
+
+def _passes(bits: int) -> int:
+    return max(1, -(-bits // NTT_MAX_PASS_BITS))
+
+
 def four_step_split(k: int, world: int) -> int:
-    """log2(n1) for a 2^k transform over `world` ranks (both factors >= world)."""
+    """log2(n1) for a 2^k transform over `world` ranks (both factors >= world): the split whose local transforms
+    need the fewest kernel passes in total, the most balanced one among those (k = 24: 2^9 x 2^15, 1 + 2 passes —
+    the balanced 2^12 x 2^12 needs 2 + 2, one more than the single-GPU transform)."""
     lw = world.bit_length() - 1
     assert world == 1 << lw, "world size must be a power of two"
-    log_n1 = (k + 1) // 2
-    assert log_n1 >= lw and k - log_n1 >= lw, "transform too small for this many ranks"
-    return log_n1
+    assert k >= 2 * lw and k >= 2, "transform too small for this many ranks"
+    lo = max(lw, 1)
+    return min(range(lo, k - lo + 1), key=lambda a: (_passes(a) + _passes(k - a), abs(2 * a - k), a))
 
 
 def column_block(a: np.ndarray, k: int, log_n1: int, world: int, rank: int) -> np.ndarray:

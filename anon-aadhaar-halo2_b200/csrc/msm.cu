@@ -607,6 +607,9 @@ __device__ __forceinline__ uint32_t find_key(const uint32_t* __restrict__ start,
     return lo;
 }
 
+// (Tried in round 2: the ten products of the mixed addition as calls of one __noinline__ multiplication / squaring
+// body instead of ten inlined copies, to shrink the ~37 KB loop body: 2 950 instead of 4 300 SASS instructions, but
+// 244 MOV + 226 SEL of argument marshalling and 2x the spills: 33.9 ms against 32.1 ms at 2^24.  Not kept.)
 // ADD = false: buckets were cleared, a closed run is stored.  ADD = true (a later point range of the
 // same MSM, b200zk_msm_g1_registered's upload pipeline): a run that closes inside the chunk
 // continues from what the earlier ranges left in the bucket.
@@ -1057,8 +1060,15 @@ static uint32_t g_msm_force_c = 0;
 // upload pipeline of b200zk_msm_g1_registered (one large host-side commit): number of point
 // ranges and the size from which it is used
 constexpr size_t MSM_MAX_PARTS = 16;
-static size_t g_msm_pipe_parts = getenv("B200ZK_MSM_PIPE_PARTS") ? (size_t)atoi(getenv("B200ZK_MSM_PIPE_PARTS")) : 4;
-static size_t g_msm_pipe_min_n = getenv("B200ZK_MSM_PIPE_MIN_N") ? (size_t)atoll(getenv("B200ZK_MSM_PIPE_MIN_N")) : ((size_t)1 << 22);
+// measured at 2^24 (scratch/r2_e2e_commit.py; device-resident commit 38.8 ms): 4 equal ranges 43.9 ms; ranges of
+// 1/21, 4/21, 16/21 of the points 41.0 ms; (parts, growth) = (3, 3) 41.4, (4, 4) 41.2, (3, 5) 41.7, (4, 2) 42.3, (2, 8) 44.7
+constexpr size_t MSM_PIPE_PARTS_DEFAULT = 3;
+constexpr size_t MSM_PIPE_MIN_N_DEFAULT = (size_t)1 << 22;
+static size_t g_msm_pipe_parts = getenv("B200ZK_MSM_PIPE_PARTS") ? (size_t)atoi(getenv("B200ZK_MSM_PIPE_PARTS")) : MSM_PIPE_PARTS_DEFAULT;
+static size_t g_msm_pipe_min_n = getenv("B200ZK_MSM_PIPE_MIN_N") ? (size_t)atoll(getenv("B200ZK_MSM_PIPE_MIN_N")) : MSM_PIPE_MIN_N_DEFAULT;
+// ratio of consecutive range lengths: the copy of a range takes ~1/4 of the time its sort + accumulation does, so a
+// short first range (little to wait for) followed by ranges growing by that factor keeps the copy ahead of the compute
+static double g_msm_pipe_growth = getenv("B200ZK_MSM_PIPE_GROWTH") ? atof(getenv("B200ZK_MSM_PIPE_GROWTH")) : 4.0;
 static cudaStream_t g_msm_copy_stream = nullptr;
 static cudaEvent_t g_msm_part_ev[MSM_MAX_PARTS + 1];
 static void msm_release_pipeline() {          // b200zk_shutdown: the next init may bind another device
@@ -1237,6 +1247,9 @@ __global__ void __launch_bounds__(256) msm_group_sum_kernel(const G1Xyzz* __rest
 struct MsmPart {
     bool first = true, last = true;
     uint32_t index_offset = 0;
+    // length of the longest range of this MSM: every range sizes the work arena for it, so that the arena — whose
+    // head holds the buckets the ranges share — never has to grow (and move) between two ranges
+    size_t longest = 0;
 };
 
 static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, size_t count,
@@ -1282,12 +1295,15 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     const size_t o_bsum = carve(((size_t)scan_blocks + 1) * 4);
     const size_t o_total = carve(256);
     const size_t o_run = carve(sizeof(MsmRun));
-    const size_t o_sorted = carve(max_pairs * 4);
-    const size_t o_digits = carve(max_pairs * 4);
+    const size_t pairs_cap = std::max(n, part.longest) * nwin * count;
+    const size_t o_sorted = carve(pairs_cap * 4);
+    const size_t o_digits = carve(pairs_cap * 4);
     // two-level partition sort (large inputs): 8-byte records + the partition tables
-    const bool psort = g_msm_psort && max_pairs >= g_msm_psort_min_pairs && nkeys <= ((size_t)PSORT_MAX_PARTS << PSORT_MAX_SHIFT);
-    const size_t o_rec = carve(psort ? max_pairs * 8 : 0);
-    const size_t o_ptab = carve(psort ? (size_t)(4 * (PSORT_MAX_PARTS + 1)) * 4 : 0);
+    const bool psort_fits = g_msm_psort && nkeys <= ((size_t)PSORT_MAX_PARTS << PSORT_MAX_SHIFT);
+    const bool psort = psort_fits && max_pairs >= g_msm_psort_min_pairs;
+    const bool psort_cap = psort_fits && pairs_cap >= g_msm_psort_min_pairs;
+    const size_t o_rec = carve(psort_cap ? pairs_cap * 8 : 0);
+    const size_t o_ptab = carve(psort_cap ? (size_t)(4 * (PSORT_MAX_PARTS + 1)) * 4 : 0);
     char* base = (char*)c.scratch(s).msm_work.get(off);
     uint32_t* hist = (uint32_t*)(base + o_hist);
     uint32_t* start = (uint32_t*)(base + o_start);
@@ -1594,20 +1610,38 @@ static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stri
             ZK_CUDA(cudaStreamCreateWithFlags(&g_msm_copy_stream, cudaStreamNonBlocking));
             for (auto& e : g_msm_part_ev) ZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
-        const size_t per = align_up((n + parts - 1) / parts, 256);
+        // range lengths in geometric progression (growth 1: equal ranges), multiples of 256 points
+        size_t begin_of[MSM_MAX_PARTS + 1];
+        size_t nparts = 0;
+        {
+            const double g = std::max(1.0, g_msm_pipe_growth);
+            double sum = 0, w = 1;
+            for (size_t p = 0; p < parts; ++p, w *= g) sum += w;
+            size_t b = 0;
+            w = 1;
+            for (size_t p = 0; p < parts && b < n; ++p, w *= g) {
+                size_t len = p + 1 == parts ? n - b : align_up((size_t)((double)n * (w / sum)) + 1, 256);
+                len = std::min(len, n - b);
+                begin_of[nparts++] = b;
+                b += len;
+            }
+            begin_of[nparts] = n;
+        }
+        size_t longest = 0;
+        for (size_t p = 0; p < nparts; ++p) longest = std::max(longest, begin_of[p + 1] - begin_of[p]);
         ZK_CUDA(cudaEventRecord(g_msm_part_ev[MSM_MAX_PARTS], s));   // earlier users of the staging buffer
         ZK_CUDA(cudaStreamWaitEvent(g_msm_copy_stream, g_msm_part_ev[MSM_MAX_PARTS], 0));
-        size_t nparts = 0;
-        for (size_t b = 0; b < n; b += per, ++nparts) {
-            const size_t len = std::min(per, n - b);
+        for (size_t p = 0; p < nparts; ++p) {
+            const size_t b = begin_of[p], len = begin_of[p + 1] - b;
             ZK_CUDA(cudaMemcpyAsync(ds + b, scalars + 4 * b, len * sizeof(Fr), cudaMemcpyHostToDevice, g_msm_copy_stream));
-            ZK_CUDA(cudaEventRecord(g_msm_part_ev[nparts], g_msm_copy_stream));
+            ZK_CUDA(cudaEventRecord(g_msm_part_ev[p], g_msm_copy_stream));
         }
         for (size_t p = 0; p < nparts; ++p) {
-            const size_t b = p * per, len = std::min(per, n - b);
+            const size_t b = begin_of[p], len = begin_of[p + 1] - b;
             ZK_CUDA(cudaStreamWaitEvent(s, g_msm_part_ev[p], 0));
             MsmPart part;
             part.first = p == 0; part.last = p + 1 == nparts; part.index_offset = (uint32_t)b;
+            part.longest = longest;
             msm_device(c, ds + b, len, 1, t->d, len, &pre, dout, s, part);
         }
         ZK_CUDA(cudaMemcpyAsync(out_xyz, dout, sizeof(G1Jacobian), cudaMemcpyDeviceToHost, s));
@@ -1683,9 +1717,9 @@ int b200zk_msm_tune(uint32_t max_chunk, uint32_t max_seglen, uint32_t force_wind
 
 int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n) {
     return guarded([&] {
-        ZK_REQUIRE(parts >= 1 && parts <= MSM_MAX_PARTS, "parts out of range");
-        g_msm_pipe_parts = parts;
-        g_msm_pipe_min_n = min_n;
+        ZK_REQUIRE(parts <= MSM_MAX_PARTS, "parts out of range");
+        g_msm_pipe_parts = parts ? parts : MSM_PIPE_PARTS_DEFAULT;      // 0: the library's defaults
+        g_msm_pipe_min_n = parts ? min_n : MSM_PIPE_MIN_N_DEFAULT;
     });
 }
 

@@ -376,7 +376,9 @@ int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]);
 /* Upload pipeline of b200zk_msm_g1_registered: a single host-side commit of at least `min_n`
  * scalars against a window table is fed in `parts` point ranges that share one bucket set, so
  * the PCIe upload of range p+1 runs under the sort + accumulation of range p (same group
- * element).  parts = 1 disables it.  Defaults: 4 parts from 2^22 scalars. */
+ * element).  The ranges grow geometrically (each 4x the one before: a short first range so that
+ * little has to arrive before the GPU starts, the copy being ~4x faster than the computation it
+ * feeds).  parts = 1 disables it; parts = 0 restores the defaults: 3 ranges from 2^22 scalars. */
 int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n);
 /* Transfer pipeline of b200zk_ntt / b200zk_intt on one host buffer of at least 2^min_log_n
  * elements: the first pass runs in `chunks` column ranges, each as soon as its rectangle of the

@@ -102,7 +102,7 @@ def test_shutdown_and_reinit_with_pipelines(zk):
             zk.best_fft(a, w, k)
             return got_pt, a
         finally:
-            zk.check(lib.b200zk_msm_upload_pipeline(4, 1 << 22))
+            zk.check(lib.b200zk_msm_upload_pipeline(0, 0))
             zk.check(lib.b200zk_ntt_transfer_pipeline(4, 22))
 
     for _ in range(2):

@@ -220,7 +220,7 @@ def test_commit_upload_pipeline_same_point(zk, parts, n):
         piped = jac_affine(params.commit(s))
         piped_short = jac_affine(params.commit(s[: n - 3]))          # ragged last range, fewer scalars than bases
     finally:
-        zk.check(lib.b200zk_msm_upload_pipeline(4, 1 << 22))
+        zk.check(lib.b200zk_msm_upload_pipeline(0, 0))
         params.close()
     assert one_shot == want
     assert piped == want

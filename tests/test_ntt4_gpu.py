@@ -36,7 +36,7 @@ class _OneGpuRanks:
         return None
 
 
-@pytest.mark.parametrize("k,world", [(4, 1), (6, 2), (9, 2), (10, 4), (13, 8), (16, 4)])
+@pytest.mark.parametrize("k,world", [(4, 1), (6, 2), (9, 2), (10, 4), (13, 8), (16, 4), (19, 4), (20, 8), (21, 2)])
 def test_four_step_matches_best_fft(zk, k, world):
     from b200zk import sharding
     from b200zk.api import FR_MODULUS, FR_ROOT_OF_UNITY

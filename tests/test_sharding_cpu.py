@@ -105,6 +105,22 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def test_four_step_split_minimises_kernel_passes():
+    """Both factors at least the world size, the fewest transform-kernel passes (<= 2^9 points each), balanced
+    among equals: k = 24 is 2^9 x 2^15 (1 + 2 passes, as many as the single-GPU transform), small k stays k / 2."""
+    from b200zk import sharding
+    for world in (1, 2, 4, 8):
+        lw = world.bit_length() - 1
+        for k in range(max(2, 2 * lw), 29):
+            a = sharding.four_step_split(k, world)
+            assert a >= max(lw, 1) and k - a >= max(lw, 1)
+            best = min(sharding._passes(b) + sharding._passes(k - b) for b in range(max(lw, 1), k - max(lw, 1) + 1))
+            assert sharding._passes(a) + sharding._passes(k - a) == best
+            if k <= 18:
+                assert a == k // 2
+    assert sharding.four_step_split(24, 8) == 9 and sharding.four_step_split(26, 8) == 9
+
+
 def test_two_rank_gloo_msm_split_and_h_gather():
     import torch.multiprocessing as mp
 
