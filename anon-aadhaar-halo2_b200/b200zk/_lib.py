@@ -66,6 +66,7 @@ def load() -> C.CDLL:
         "b200zk_coeff_to_coset_dev": ([vp, sz, vp, sz, sz, u32, vp, vp, vp], C.c_int),
         "b200zk_extended_coset_slice_dev": ([vp, sz, vp, sz, sz, u32, u32, u32, vp], C.c_int),
         "b200zk_extended_coset_interleave_dev": ([vp, vp, u32, u32, u32, vp], C.c_int),
+        "b200zk_ntt4_first_pass_scatter_dev": ([vp, u32, u32, vp, u32, u32, vp, sz, sz, vp], C.c_int),
         "b200zk_ntt4_twiddle_scatter_dev": ([vp, u32, u32, vp, u32, u32, vp, sz, sz, vp], C.c_int),
         "b200zk_ntt4_gather_rows_dev": ([vp, vp, u32, u32, u32, vp], C.c_int),
         "b200zk_msm_g1": ([vp, vp, sz, vp], C.c_int),

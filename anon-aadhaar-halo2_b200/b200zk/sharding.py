@@ -137,22 +137,27 @@ def _passes(bits: int) -> int:
 
 
 def four_step_split(k: int, world: int) -> int:
-    """log2(n1) for a 2^k transform over `world` ranks (both factors >= world): the split whose local transforms
-    need the fewest kernel passes in total, the most balanced one among those (k = 24: 2^9 x 2^15, 1 + 2 passes —
-    the balanced 2^12 x 2^12 needs 2 + 2, one more than the single-GPU transform)."""
+    """log2(n1) for a 2^k transform over `world` ranks (both factors >= world, n1 <= 2^9 so that the first step is one
+    kernel pass): the split whose local transforms need the fewest kernel passes in total — k = 24: 2^8 x 2^16, 1 + 2
+    passes, as many as the single-GPU transform (a balanced 2^12 x 2^12 needs 2 + 2) — and among those the balanced one
+    up to k = 18, the one with 8-bit first passes (the single-GPU plan's width) above."""
     lw = world.bit_length() - 1
     assert world == 1 << lw, "world size must be a power of two"
     assert k >= 2 * lw and k >= 2, "transform too small for this many ranks"
     lo = max(lw, 1)
-    return min(range(lo, k - lo + 1), key=lambda a: (_passes(a) + _passes(k - a), abs(2 * a - k), a))
+    hi = min(k - lo, NTT_MAX_PASS_BITS)
+    assert hi >= lo, "transform too large for this many ranks"
+    target = k // 2 if k <= 2 * NTT_MAX_PASS_BITS else 8
+    return min(range(lo, hi + 1), key=lambda a: (_passes(a) + _passes(k - a), abs(a - target), a))
 
 
 def column_block(a: np.ndarray, k: int, log_n1: int, world: int, rank: int) -> np.ndarray:
-    """Rank's input share of a natural-order vector a (n, 4): X[j2 - r m][j1] = a[j1 n2 + j2]."""
+    """Rank's input share of a natural-order vector a (n, 4): its columns of the [n1][n2] matrix,
+    X[j1][j2 - r m] = a[j1 n2 + j2]."""
     n1, n2 = 1 << log_n1, 1 << (k - log_n1)
     m = n2 // world
     mat = a.reshape(n1, n2, 4)
-    return np.ascontiguousarray(mat[:, rank * m:(rank + 1) * m].transpose(1, 0, 2))
+    return np.ascontiguousarray(mat[:, rank * m:(rank + 1) * m])
 
 
 def natural_from_row_blocks(blocks, k: int, log_n1: int) -> np.ndarray:
@@ -165,18 +170,19 @@ def natural_from_row_blocks(blocks, k: int, log_n1: int) -> np.ndarray:
 
 def sharded_best_fft(x_local, k: int, omega: int, ops, world: int, rank: int):
     """`best_fft` of 2^k elements over `world` ranks.  `x_local` is this rank's column block
-    ([m][n1], see column_block); the result is its row block ([n1 / world][n2]).  `ops`
+    ([n1][m], see column_block); the result is its row block ([n1 / world][n2]).  `ops`
     supplies the local steps and the exchange (DeviceFourStep below on GPUs; the CPU tests
     inject the oracle):
-        ops.ntt_rows(buf, count, log_len, omega)     in-place transforms of contiguous rows
-        ops.twiddle_exchange(buf, k, log_n1, omega)  -> this rank's [n1 / world][n2] row block
+        ops.first_pass_exchange(buf, k, log_n1, omega)  n1-point transforms down the columns, twiddle
+                                                        omega^(i1 j2), exchange -> this rank's
+                                                        [n1 / world][n2] row block
+        ops.ntt_rows(buf, count, log_len, omega)        in-place transforms of contiguous rows
     """
     from .api import FR_MODULUS
     log_n1 = four_step_split(k, world)
     log_n2 = k - log_n1
-    n1, n2 = 1 << log_n1, 1 << log_n2
-    ops.ntt_rows(x_local, n2 // world, log_n1, pow(omega, n2, FR_MODULUS))
-    rows = ops.twiddle_exchange(x_local, k, log_n1, omega)
+    n1 = 1 << log_n1
+    rows = ops.first_pass_exchange(x_local, k, log_n1, omega)
     ops.ntt_rows(rows, n1 // world, log_n2, pow(omega, n1, FR_MODULUS))
     return rows
 
@@ -184,9 +190,10 @@ def sharded_best_fft(x_local, k: int, omega: int, ops, world: int, rank: int):
 class DeviceFourStep:
     """Device implementation of the two local steps and the exchange.  Buffers are torch
     int64 CUDA tensors (4 limbs per element).  Exchange modes:
-      * "p2p"  : the twiddle kernel stores straight into the peers' row buffers through
-                 symmetric-memory mappings (NVLink / NVSwitch); no separate collective;
-      * "nccl" : the twiddle kernel packs per-destination chunks, `all_to_all_single`
+      * "p2p"  : the first transform pass stores straight into the peers' row buffers through
+                 symmetric-memory mappings (NVLink / NVSwitch): one kernel is local transform,
+                 twiddle and all-to-all; no separate collective;
+      * "nccl" : the same kernel packs per-destination chunks, `all_to_all_single`
                  moves them, a strided copy lays the rows out."""
 
     def __init__(self, k: int, world: int, rank: int, device, mode: str = "auto"):
@@ -254,11 +261,11 @@ class DeviceFourStep:
             self.check(self.lib.b200zk_ntt_dev(self.C.c_void_p(buf.data_ptr()), 1 << log_len, count, log_len, _ptr(w),
                                                None, self._stream()))
 
-    def twiddle_exchange(self, buf, k: int, log_n1: int, omega: int):
+    def first_pass_exchange(self, buf, k: int, log_n1: int, omega: int):
         with self._Ordered(self):
-            return self._twiddle_exchange(buf, k, log_n1, omega)
+            return self._first_pass_exchange(buf, k, log_n1, omega)
 
-    def _twiddle_exchange(self, buf, k: int, log_n1: int, omega: int):
+    def _first_pass_exchange(self, buf, k: int, log_n1: int, omega: int):
         from .api import _ptr, fr_limbs
         C, world, rank = self.C, self.world, self.rank
         n1, n2 = 1 << log_n1, 1 << (k - log_n1)
@@ -272,7 +279,7 @@ class DeviceFourStep:
             self.turn ^= 1
             for s in range(world):
                 bases[s] = self.peer_ptrs2[turn][s]
-            self.check(self.lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(buf.data_ptr()), k, log_n1, _ptr(w), world,
+            self.check(self.lib.b200zk_ntt4_first_pass_scatter_dev(C.c_void_p(buf.data_ptr()), k, log_n1, _ptr(w), world,
                                                                 rank, bases, n2, rank * m, self._stream()))
             self.hdl2[turn].barrier(channel=0)   # every peer's stores into my rows have landed
             self.rows = self.rows2[turn]
@@ -280,7 +287,7 @@ class DeviceFourStep:
         dst = self.send if world > 1 else self.rows
         for s in range(world):
             bases[s] = dst.data_ptr() + s * rows * m * 32
-        self.check(self.lib.b200zk_ntt4_twiddle_scatter_dev(C.c_void_p(buf.data_ptr()), k, log_n1, _ptr(w), world, rank,
+        self.check(self.lib.b200zk_ntt4_first_pass_scatter_dev(C.c_void_p(buf.data_ptr()), k, log_n1, _ptr(w), world, rank,
                                                             bases, m, 0, self._stream()))
         if world == 1:
             return self.rows

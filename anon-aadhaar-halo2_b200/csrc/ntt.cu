@@ -142,28 +142,28 @@ struct NttMods {
     uint64_t n_keep = 0;  // 0 = keep all
 };
 
-template <int B, bool FIRST> static void launch_pass(const NttPassArgs& a, unsigned blocks, unsigned batch, cudaStream_t s) {
+template <int B, int MODE> static void launch_pass(const NttPassArgs& a, unsigned blocks, unsigned batch, cudaStream_t s) {
     static int configured_device = -1;      // the attribute is per device (b200zk_shutdown + init may rebind)
     constexpr int smem = 2 * NTT_TILE * sizeof(uint4);
     if (configured_device != ctx().device) {
-        ZK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<B, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ZK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<B, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured_device = ctx().device;
     }
-    ntt_pass_kernel<B, FIRST><<<dim3(blocks, batch), NTT_THREADS, smem, s>>>(a);
+    ntt_pass_kernel<B, MODE><<<dim3(blocks, batch), NTT_THREADS, smem, s>>>(a);
     ZK_LAUNCH_CHECK();
 }
 
-template <bool FIRST> static void launch_pass_b(int b, const NttPassArgs& a, unsigned blocks, unsigned batch, cudaStream_t s) {
+template <int MODE> static void launch_pass_b(int b, const NttPassArgs& a, unsigned blocks, unsigned batch, cudaStream_t s) {
     switch (b) {
-        case 1: launch_pass<1, FIRST>(a, blocks, batch, s); break;
-        case 2: launch_pass<2, FIRST>(a, blocks, batch, s); break;
-        case 3: launch_pass<3, FIRST>(a, blocks, batch, s); break;
-        case 4: launch_pass<4, FIRST>(a, blocks, batch, s); break;
-        case 5: launch_pass<5, FIRST>(a, blocks, batch, s); break;
-        case 6: launch_pass<6, FIRST>(a, blocks, batch, s); break;
-        case 7: launch_pass<7, FIRST>(a, blocks, batch, s); break;
-        case 8: launch_pass<8, FIRST>(a, blocks, batch, s); break;
-        case 9: launch_pass<9, FIRST>(a, blocks, batch, s); break;
+        case 1: launch_pass<1, MODE>(a, blocks, batch, s); break;
+        case 2: launch_pass<2, MODE>(a, blocks, batch, s); break;
+        case 3: launch_pass<3, MODE>(a, blocks, batch, s); break;
+        case 4: launch_pass<4, MODE>(a, blocks, batch, s); break;
+        case 5: launch_pass<5, MODE>(a, blocks, batch, s); break;
+        case 6: launch_pass<6, MODE>(a, blocks, batch, s); break;
+        case 7: launch_pass<7, MODE>(a, blocks, batch, s); break;
+        case 8: launch_pass<8, MODE>(a, blocks, batch, s); break;
+        case 9: launch_pass<9, MODE>(a, blocks, batch, s); break;
         default: throw Error{"b200zk: bad pass width"};
     }
 }
@@ -235,12 +235,12 @@ static void ntt_run(Context& c, const Fr* in, uint64_t in_stride, Fr* out, uint6
             for (int ch = 0; ch < hooks->chunks; ++ch) {
                 a.block_offset = (uint32_t)ch * per;
                 if (p == 0 && hooks->before_first) hooks->before_first(ch, (uint64_t)a.block_offset * C, (uint64_t)per * C, (uint64_t)1 << b);
-                if (p == 0) launch_pass_b<true>(b, a, per, (unsigned)count, s);
-                else launch_pass_b<false>(b, a, per, (unsigned)count, s);
+                if (p == 0) launch_pass_b<1>(b, a, per, (unsigned)count, s);
+                else launch_pass_b<0>(b, a, per, (unsigned)count, s);
                 if (p == P - 1 && hooks->after_last) hooks->after_last(ch, (uint64_t)a.block_offset * C, (uint64_t)per * C, (uint64_t)1 << b);
             }
-        } else if (p == 0) launch_pass_b<true>(b, a, blocks, (unsigned)count, s);
-        else launch_pass_b<false>(b, a, blocks, (unsigned)count, s);
+        } else if (p == 0) launch_pass_b<1>(b, a, blocks, (unsigned)count, s);
+        else launch_pass_b<0>(b, a, blocks, (unsigned)count, s);
         src = dst;
         src_stride = dst_stride;
         log_I += b;
@@ -715,6 +715,61 @@ int b200zk_ntt4_twiddle_scatter_dev(const void* d_in, uint32_t log_n, uint32_t l
         const uint32_t n1 = 1u << log_n1, m = 1u << a.log_m;
         ntt4_twiddle_scatter_kernel<<<dim3((n1 + 31) / 32, (m + 31) / 32), 256, 0, s>>>(a);
         ZK_LAUNCH_CHECK();
+    });
+}
+
+int b200zk_ntt4_first_pass_scatter_dev(const void* d_in, uint32_t log_n, uint32_t log_n1, const uint64_t omega[4],
+                                       uint32_t world, uint32_t rank, void* const* dest_bases, size_t dest_pitch,
+                                       size_t dest_col_offset, void* stream) {
+    return guarded([&] {
+        ZK_REQUIRE(d_in && omega && dest_bases, "null argument");
+        ZK_REQUIRE(world >= 1 && world <= 8 && (world & (world - 1)) == 0 && rank < world, "world must be 1, 2, 4 or 8");
+        ZK_REQUIRE(log_n >= 2 && log_n <= 28 && log_n1 >= 1 && log_n1 < log_n, "bad transform split");
+        ZK_REQUIRE(log_n1 <= NTT_MAX_B, "the first factor must fit one pass of the transform kernel");
+        uint32_t log_w = 0;
+        while ((1u << log_w) < world) ++log_w;
+        const uint32_t log_n2 = log_n - log_n1;
+        ZK_REQUIRE(log_n1 >= log_w && log_n2 >= log_w, "both factors must be at least the world size");
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = stream ? (cudaStream_t)stream : c.stream;
+        // The local step is pass 0 of the whole 2^log_n transform restricted to this rank's columns: n1-point
+        // transforms along the rows of the [n1][m] slab (tile twiddles of a 2^log_n1 transform with root omega^n2),
+        // the inter-pass twiddle omega^(i1 * j2) of the whole transform, and the store goes to the owner of row i1.
+        const Fr w = fr_from_limbs(omega);
+        NttTables* big = ntt_get_tables(c, w, log_n, s);
+        NttTables* small = ntt_get_tables(c, w.pow_u64((uint64_t)1 << log_n2), log_n1, s);
+        ZK_REQUIRE(small->npass == 1 && small->bits[0] == (int)log_n1, "unexpected pass plan");
+        const uint32_t log_m = log_n2 - log_w;
+        NttPassArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = (const Fr*)d_in;
+        a.out = nullptr;
+        a.log_n = log_n;
+        a.log_I = 0;
+        a.log_cols = log_m;
+        a.last = 0;
+        a.tw_tile = small->tw_tile[log_n1];
+        a.tw_lo = big->tw_lo;
+        a.tw_hi = big->tw_hi;
+        a.tw_h = big->tw_h;
+        a.tw_direct = big->tw_direct[0];
+        a.w8[0] = small->w8[0]; a.w8[1] = small->w8[1]; a.w8[2] = small->w8[2];
+        a.in_mode = NTT_IN_PLAIN;
+        a.n_in = 1u << (log_n1 + log_m);
+        a.out_mode = NTT_OUT_PLAIN;
+        a.n_keep = a.n_in;
+        a.col_base = rank << log_m;
+        a.scatter_log_rows = log_n1 - log_w;
+        a.scatter_pitch = dest_pitch;
+        a.scatter_col_offset = dest_col_offset;
+        for (uint32_t i = 0; i < world; ++i) {
+            ZK_REQUIRE(dest_bases[i], "null destination buffer");
+            a.scatter_dest[i] = (Fr*)dest_bases[i];
+        }
+        const uint32_t C = 1u << (NTT_TILE_LOG - log_n1);
+        const unsigned blocks = ((1u << log_m) + C - 1) / C;
+        launch_pass_b<2>((int)log_n1, a, blocks, 1, s);
     });
 }
 

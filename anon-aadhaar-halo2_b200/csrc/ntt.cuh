@@ -65,6 +65,14 @@ struct NttPassArgs {
     uint64_t out_batch_stride;
     uint32_t block_offset;      // first column tile of this launch (a pass may be launched in column ranges)
     const Fr* tw_direct;        // omega^(x << log_I) for every x = i_p * J this pass can form, or null (lo / hi tables)
+    // first pass of a transform sharded over several GPUs (b200zk_ntt4_first_pass_scatter_dev): `in` is this rank's
+    // [2^b][2^log_cols] slab of columns col_base .. col_base + 2^log_cols of the whole transform, and output (i_p, column)
+    // is stored at scatter_dest[i_p >> scatter_log_rows] + (i_p mod 2^scatter_log_rows) * scatter_pitch + scatter_col_offset
+    // + (column - col_base): row i_p of the rank that owns it (a peer mapping, or a slice of a local send buffer)
+    uint32_t col_base;
+    uint32_t scatter_log_rows;
+    uint64_t scatter_pitch, scatter_col_offset;
+    Fr* scatter_dest[8];
 };
 
 // Per-(omega, log_n) twiddle tables, built on the device once and cached (ntt.cu).
@@ -167,10 +175,13 @@ template <int B> struct NttRounds {
     }
 };
 
-template <int B, bool FIRST, int Q>
+// MODE 0: a later pass; 1: the first pass (input modifiers, contiguous tile output); 2: the first pass of a transform
+// sharded over several GPUs (outputs scattered to the owners of their rows)
+template <int B, int MODE, int Q>
 __device__ __forceinline__ void ntt_round(const NttPassArgs& A, const Fr* __restrict__ in, Fr* __restrict__ out,
                                           uint4* S0, uint4* S1, uint32_t tid, uint32_t m0) {
     using RD = NttRounds<B>;
+    constexpr bool FIRST = MODE != 0, SCATTER = MODE == 2;
     constexpr int NP = 1 << B;
     constexpr int LOGC = NTT_TILE_LOG - B;
     constexpr int C = 1 << LOGC;
@@ -251,15 +262,16 @@ __device__ __forceinline__ void ntt_round(const NttPassArgs& A, const Fr* __rest
             }
         }
     } else {
-        if constexpr (FIRST && Q > 0) __syncthreads();  // all reads of the planes done before restaging
+        if constexpr (FIRST && !SCATTER && Q > 0) __syncthreads();  // all reads of the planes done before restaging
         // ---- final: inter-pass twiddle, output modifiers, store
         Fr* stage = reinterpret_cast<Fr*>(S0);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const uint32_t m = m0 + colv[g];
             const bool colok = m < ncols;
-            const uint32_t Jv = m >> A.log_I;
-            const uint32_t Iv = m & ((1u << A.log_I) - 1u);
+            const uint32_t mg = SCATTER ? m + A.col_base : m;    // column of the whole transform
+            const uint32_t Jv = mg >> A.log_I;
+            const uint32_t Iv = mg & ((1u << A.log_I) - 1u);
 #pragma unroll
             for (int a = 0; a < SQ; ++a) {
                 const int c = bitrev_c<RQ>(a);
@@ -294,7 +306,12 @@ __device__ __forceinline__ void ntt_round(const NttPassArgs& A, const Fr* __rest
                         x = x * (r3 == 0 ? A.out_tab[0] : (r3 == 1 ? A.out_tab[1] : A.out_tab[2]));
                     }
                     if (A.last) x = x.canon();   // values leave the library fully reduced
-                    if constexpr (FIRST) {
+                    if constexpr (SCATTER) {
+                        // eight (2^(11 - b)) consecutive lanes hold consecutive columns of row i_p: 256-byte runs
+                        Fr* q = A.scatter_dest[ip >> A.scatter_log_rows] +
+                                (uint64_t)(ip & ((1u << A.scatter_log_rows) - 1u)) * A.scatter_pitch + A.scatter_col_offset + m;
+                        st_fr(q, x);
+                    } else if constexpr (FIRST) {
                         st_fr(stage + (colv[g] << B) + ip, x);
                     } else {
                         if (!A.last || oi < A.n_keep) st_fr(out + oi, x);
@@ -302,7 +319,7 @@ __device__ __forceinline__ void ntt_round(const NttPassArgs& A, const Fr* __rest
                 }
             }
         }
-        if constexpr (FIRST) {
+        if constexpr (FIRST && !SCATTER) {
             // tile output is one contiguous block [m0 * NP, (m0 + C) * NP) of `out`
             __syncthreads();
             const uint32_t vcols = (ncols - m0 < (uint32_t)C) ? (ncols - m0) : (uint32_t)C;
@@ -319,17 +336,17 @@ __device__ __forceinline__ void ntt_round(const NttPassArgs& A, const Fr* __rest
     }
 }
 
-template <int B, bool FIRST, int Q>
+template <int B, int MODE, int Q>
 __device__ __forceinline__ void ntt_rounds_from(const NttPassArgs& A, const Fr* in, Fr* out, uint4* S0, uint4* S1,
                                                 uint32_t tid, uint32_t m0) {
-    ntt_round<B, FIRST, Q>(A, in, out, S0, S1, tid, m0);
+    ntt_round<B, MODE, Q>(A, in, out, S0, S1, tid, m0);
     if constexpr (Q + 1 < NttRounds<B>::NR) {
         __syncthreads();
-        ntt_rounds_from<B, FIRST, Q + 1>(A, in, out, S0, S1, tid, m0);
+        ntt_rounds_from<B, MODE, Q + 1>(A, in, out, S0, S1, tid, m0);
     }
 }
 
-template <int B, bool FIRST>
+template <int B, int MODE>
 __global__ void __launch_bounds__(NTT_THREADS, B200ZK_NTT_MIN_CTAS) ntt_pass_kernel(const __grid_constant__ NttPassArgs A) {
     extern __shared__ uint4 ntt_smem[];
     uint4* S0 = ntt_smem;
@@ -338,7 +355,7 @@ __global__ void __launch_bounds__(NTT_THREADS, B200ZK_NTT_MIN_CTAS) ntt_pass_ker
     const uint32_t m0 = (blockIdx.x + A.block_offset) << LOGC;
     const Fr* in = A.in + (uint64_t)blockIdx.y * A.in_batch_stride;
     Fr* out = A.out + (uint64_t)blockIdx.y * A.out_batch_stride;
-    ntt_rounds_from<B, FIRST, 0>(A, in, out, S0, S1, threadIdx.x, m0);
+    ntt_rounds_from<B, MODE, 0>(A, in, out, S0, S1, threadIdx.x, m0);
 }
 
 #endif  // __CUDACC__

@@ -58,6 +58,7 @@ extern "C" {
     pub fn b200zk_coeff_to_coset_dev(d_in: *const c_void, in_stride: usize, d_out: *mut c_void, out_stride: usize, count: usize, k: u32, omega: *const u64, coset_generator: *const u64, stream: *mut c_void) -> c_int;
     pub fn b200zk_extended_coset_slice_dev(d_ext: *const c_void, ext_stride: usize, d_out: *mut c_void, out_stride: usize, count: usize, k: u32, ext_k: u32, coset: u32, stream: *mut c_void) -> c_int;
     pub fn b200zk_extended_coset_interleave_dev(d_coset: *const c_void, d_ext: *mut c_void, k: u32, ext_k: u32, coset: u32, stream: *mut c_void) -> c_int;
+    pub fn b200zk_ntt4_first_pass_scatter_dev(d_in: *const c_void, log_n: u32, log_n1: u32, omega: *const u64, world: u32, rank: u32, dest_bases: *const *mut c_void, dest_pitch: usize, dest_col_offset: usize, stream: *mut c_void) -> c_int;
     pub fn b200zk_ntt4_twiddle_scatter_dev(d_in: *const c_void, log_n: u32, log_n1: u32, omega: *const u64, world: u32, rank: u32, dest_bases: *const *mut c_void, dest_pitch: usize, dest_col_offset: usize, stream: *mut c_void) -> c_int;
     pub fn b200zk_ntt4_gather_rows_dev(d_recv: *const c_void, d_out: *mut c_void, log_n: u32, log_n1: u32, world: u32, stream: *mut c_void) -> c_int;
     pub fn b200zk_msm_g1(scalars: *const u64, bases: *const u64, n: usize, out_xyz: *mut u64) -> c_int;

@@ -143,19 +143,26 @@ int b200zk_extended_coset_interleave_dev(const void* d_coset, void* d_ext, uint3
                                          void* stream);
 
 /* One best_fft of 2^log_n elements sharded over `world` (1, 2, 4 or 8) GPUs, one process per
- * GPU (SURVEY.md section 8 e).  n = n1 * n2 with n1 = 2^log_n1; rank r holds the columns
- * j2 in [r m, (r + 1) m), m = n2 / world, as d_in[j2 - r m][j1] = a[j1 * n2 + j2].  The caller
- *   1. runs b200zk_ntt_dev(d_in, n1, m, log_n1, omega^n2)                 (m transforms of n1),
- *   2. calls b200zk_ntt4_twiddle_scatter_dev: multiply by omega^(i1 * j2) and store element
- *      (i1, j2) at dest_bases[i1 / (n1 / world)] + (i1 mod (n1 / world)) * dest_pitch +
- *      dest_col_offset + (j2 - r m)   [offsets in field elements].  With peer-mapped buffers
- *      (dest_pitch = n2, dest_col_offset = r m) this pass is itself the all-to-all; with a
- *      local send buffer (dest_bases[s] = send + s * (n1 / world) * m, dest_pitch = m, offset 0)
- *      it packs for a NCCL all-to-all, whose result b200zk_ntt4_gather_rows_dev turns into
- *      the [n1 / world][n2] row block,
- *   3. runs b200zk_ntt_dev(rows, n2, n1 / world, log_n2, omega^n1): row i1 then holds
- *      A[i1 + n1 * i2] at position i2.
- * `dest_bases` is a host array of `world` device pointers. */
+ * GPU (SURVEY.md section 8 e).  n = n1 * n2 with n1 = 2^log_n1 <= 2^9; rank r holds the columns
+ * j2 in [r m, (r + 1) m), m = n2 / world, of the natural-order vector seen as an [n1][n2] matrix:
+ * d_in[j1][j2 - r m] = a[j1 * n2 + j2].
+ *   1. b200zk_ntt4_first_pass_scatter_dev — ONE kernel: the n1-point transforms along j1 (pass 0 of
+ *      the whole transform, restricted to the rank's columns), the twiddle omega^(i1 * j2), and the
+ *      exchange: element (i1, j2) is stored at dest_bases[i1 / (n1 / world)] +
+ *      (i1 mod (n1 / world)) * dest_pitch + dest_col_offset + (j2 - r m)   [offsets in field
+ *      elements].  With peer-mapped buffers (dest_pitch = n2, dest_col_offset = r m) the stores
+ *      travel over NVLink and the pass is itself the all-to-all; with a local send buffer
+ *      (dest_bases[s] = send + s * (n1 / world) * m, dest_pitch = m, offset 0) it packs for a NCCL
+ *      all-to-all, whose result b200zk_ntt4_gather_rows_dev turns into the [n1 / world][n2] row block;
+ *   2. b200zk_ntt_dev(rows, n2, n1 / world, log_n2, omega^n1): row i1 then holds A[i1 + n1 * i2] at
+ *      position i2.
+ * `dest_bases` is a host array of `world` device pointers.
+ * b200zk_ntt4_twiddle_scatter_dev is the unfused form of step 1 for a column-major slab
+ * (d_in[j2 - r m][j1], any n1): the caller first runs b200zk_ntt_dev(d_in, n1, m, log_n1, omega^n2),
+ * then this kernel multiplies by omega^(i1 * j2) and stores exactly as above. */
+int b200zk_ntt4_first_pass_scatter_dev(const void* d_in, uint32_t log_n, uint32_t log_n1, const uint64_t omega[4],
+                                       uint32_t world, uint32_t rank, void* const* dest_bases, size_t dest_pitch,
+                                       size_t dest_col_offset, void* stream);
 int b200zk_ntt4_twiddle_scatter_dev(const void* d_in, uint32_t log_n, uint32_t log_n1, const uint64_t omega[4],
                                     uint32_t world, uint32_t rank, void* const* dest_bases, size_t dest_pitch,
                                     size_t dest_col_offset, void* stream);

@@ -27,8 +27,8 @@ for mode in modes:
         torch.cuda.synchronize()
         log_n1 = sharding.four_step_split(k, world)
         n1, n2 = 1 << log_n1, 1 << (k - log_n1); m = n2 // world
-        # column block on the device: [n1][n2] -> [:, r m:(r+1) m] -> [m][n1]
-        x0 = full.view(n1, n2, 4)[:, rank * m:(rank + 1) * m].permute(1, 0, 2).contiguous().view(-1)
+        # column block on the device: [n1][n2] -> [:, r m:(r+1) m]
+        x0 = full.view(n1, n2, 4)[:, rank * m:(rank + 1) * m].contiguous().view(-1)
         ops = sharding.DeviceFourStep(k, world, rank, dev, mode=mode)
         x = x0.clone()
         rows = sharding.sharded_best_fft(x, k, omega, ops, world, rank)

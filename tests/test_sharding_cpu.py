@@ -37,15 +37,16 @@ class _CpuFourStep:
         for i in range(count):
             buf[i] = self.co.best_fft(np.ascontiguousarray(buf[i]), w, log_len, 1)
 
-    def twiddle_exchange(self, buf, k, log_n1, omega):
+    def first_pass_exchange(self, buf, k, log_n1, omega):
         import torch
         bn, world, rank = self.bn, self.world, self.rank
         n1, n2 = 1 << log_n1, 1 << (k - log_n1)
         m, rows = n2 // world, n1 // world
-        vals = [bn.fr_array_to_canonical(buf[jl]) for jl in range(m)]
+        w1 = bn.fr_array_from_canonical([pow(omega, n2, bn.R)])[0]
         send = np.zeros((world, rows, m, 4), dtype=np.uint64)
-        for jl in range(m):
-            tw = [v * pow(omega, i1 * (rank * m + jl), bn.R) % bn.R for i1, v in enumerate(vals[jl])]
+        for jl in range(m):                                      # buf is the natural [n1][m] slab
+            col = self.co.best_fft(np.ascontiguousarray(buf[:, jl]), w1, log_n1, 1)
+            tw = [v * pow(omega, i1 * (rank * m + jl), bn.R) % bn.R for i1, v in enumerate(bn.fr_array_to_canonical(col))]
             send[:, :, jl] = bn.fr_array_from_canonical(tw).reshape(world, rows, 4)
         recv = torch.empty_like(torch.from_numpy(send.view(np.int64)))
         self.dist.all_to_all_single(recv, torch.from_numpy(send.view(np.int64)))
@@ -106,19 +107,21 @@ def _worker(rank, world, port, q):
 
 
 def test_four_step_split_minimises_kernel_passes():
-    """Both factors at least the world size, the fewest transform-kernel passes (<= 2^9 points each), balanced
-    among equals: k = 24 is 2^9 x 2^15 (1 + 2 passes, as many as the single-GPU transform), small k stays k / 2."""
+    """Both factors at least the world size, the first one a single kernel pass (<= 2^9 points), the fewest passes
+    in total: k = 24 is 2^8 x 2^16 (1 + 2 passes, as many as the single-GPU transform), small k stays k / 2."""
     from b200zk import sharding
     for world in (1, 2, 4, 8):
         lw = world.bit_length() - 1
         for k in range(max(2, 2 * lw), 29):
             a = sharding.four_step_split(k, world)
             assert a >= max(lw, 1) and k - a >= max(lw, 1)
-            best = min(sharding._passes(b) + sharding._passes(k - b) for b in range(max(lw, 1), k - max(lw, 1) + 1))
+            best = min(sharding._passes(b) + sharding._passes(k - b)
+                       for b in range(max(lw, 1), min(k - max(lw, 1), sharding.NTT_MAX_PASS_BITS) + 1))
             assert sharding._passes(a) + sharding._passes(k - a) == best
+            assert a <= sharding.NTT_MAX_PASS_BITS                 # the first step is one kernel pass
             if k <= 18:
                 assert a == k // 2
-    assert sharding.four_step_split(24, 8) == 9 and sharding.four_step_split(26, 8) == 9
+    assert sharding.four_step_split(24, 8) == 8 and sharding.four_step_split(27, 8) == 9
 
 
 def test_two_rank_gloo_msm_split_and_h_gather():
