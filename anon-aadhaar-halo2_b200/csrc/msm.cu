@@ -1069,13 +1069,23 @@ static size_t g_msm_pipe_min_n = getenv("B200ZK_MSM_PIPE_MIN_N") ? (size_t)atoll
 // ratio of consecutive range lengths: the copy of a range takes ~1/4 of the time its sort + accumulation does, so a
 // short first range (little to wait for) followed by ranges growing by that factor keeps the copy ahead of the compute
 static double g_msm_pipe_growth = getenv("B200ZK_MSM_PIPE_GROWTH") ? atof(getenv("B200ZK_MSM_PIPE_GROWTH")) : 4.0;
+// Unless the schedule is pinned (environment, b200zk_msm_upload_pipeline with parts > 0) it follows the host link: every
+// piped commit times its copies and itself, and the next one uses growth = 0.9 x (commit time / copy time), in 3 ranges
+// from growth 3 up, 4 below.  One B200 alone copies ~4x faster than it computes (1/21, 4/21, 16/21); eight ranks
+// sharing the host's memory copy at 23 GB/s each, ~2x faster, and with growth 4 the last range arrived 8 ms late
+// (e2e step at 8 GPUs 73 -> 81 ms).
+static bool g_msm_pipe_auto = !getenv("B200ZK_MSM_PIPE_GROWTH") && !getenv("B200ZK_MSM_PIPE_PARTS");
+static double g_msm_pipe_ratio = 0.0;       // commit time / copy time of the previous piped commits (0: not measured yet)
+static cudaEvent_t g_msm_time_ev[4];        // copies begin / end, commit begin / end
 static cudaStream_t g_msm_copy_stream = nullptr;
 static cudaEvent_t g_msm_part_ev[MSM_MAX_PARTS + 1];
 static void msm_release_pipeline() {          // b200zk_shutdown: the next init may bind another device
     if (!g_msm_copy_stream) return;
     cudaStreamDestroy(g_msm_copy_stream);
     for (auto& e : g_msm_part_ev) cudaEventDestroy(e);
+    for (auto& e : g_msm_time_ev) cudaEventDestroy(e);
     g_msm_copy_stream = nullptr;
+    g_msm_pipe_ratio = 0.0;
 }
 static void msm_release_stage_events();
 static uint32_t g_msm_chunk_div_small = getenv("B200ZK_MSM_CHUNK_DIV_SMALL") ? (uint32_t)atoi(getenv("B200ZK_MSM_CHUNK_DIV_SMALL")) : 512u;
@@ -1604,17 +1614,23 @@ static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stri
     MsmPre pre{t->table, t->n, t->c, t->nwin};
     // One large commit with a window table: feed it in point ranges that share the bucket set,
     // so the upload of range p+1 runs under the sort + accumulation of range p.
-    const size_t parts = (count == 1 && !resident && t->table && n >= g_msm_pipe_min_n) ? std::min<size_t>(g_msm_pipe_parts, MSM_MAX_PARTS) : 1;
+    size_t parts = (count == 1 && !resident && t->table && n >= g_msm_pipe_min_n) ? std::min<size_t>(g_msm_pipe_parts, MSM_MAX_PARTS) : 1;
     if (parts > 1) {
         if (!g_msm_copy_stream) {
             ZK_CUDA(cudaStreamCreateWithFlags(&g_msm_copy_stream, cudaStreamNonBlocking));
             for (auto& e : g_msm_part_ev) ZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            for (auto& e : g_msm_time_ev) ZK_CUDA(cudaEventCreate(&e));
+        }
+        double growth = std::max(1.0, g_msm_pipe_growth);
+        if (g_msm_pipe_auto && g_msm_pipe_ratio > 0.0) {
+            growth = std::min(4.0, std::max(1.0, 0.9 * g_msm_pipe_ratio));
+            parts = growth >= 3.0 ? 3 : 4;
         }
         // range lengths in geometric progression (growth 1: equal ranges), multiples of 256 points
         size_t begin_of[MSM_MAX_PARTS + 1];
         size_t nparts = 0;
         {
-            const double g = std::max(1.0, g_msm_pipe_growth);
+            const double g = growth;
             double sum = 0, w = 1;
             for (size_t p = 0; p < parts; ++p, w *= g) sum += w;
             size_t b = 0;
@@ -1631,11 +1647,14 @@ static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stri
         for (size_t p = 0; p < nparts; ++p) longest = std::max(longest, begin_of[p + 1] - begin_of[p]);
         ZK_CUDA(cudaEventRecord(g_msm_part_ev[MSM_MAX_PARTS], s));   // earlier users of the staging buffer
         ZK_CUDA(cudaStreamWaitEvent(g_msm_copy_stream, g_msm_part_ev[MSM_MAX_PARTS], 0));
+        ZK_CUDA(cudaEventRecord(g_msm_time_ev[0], g_msm_copy_stream));
+        ZK_CUDA(cudaEventRecord(g_msm_time_ev[2], s));
         for (size_t p = 0; p < nparts; ++p) {
             const size_t b = begin_of[p], len = begin_of[p + 1] - b;
             ZK_CUDA(cudaMemcpyAsync(ds + b, scalars + 4 * b, len * sizeof(Fr), cudaMemcpyHostToDevice, g_msm_copy_stream));
             ZK_CUDA(cudaEventRecord(g_msm_part_ev[p], g_msm_copy_stream));
         }
+        ZK_CUDA(cudaEventRecord(g_msm_time_ev[1], g_msm_copy_stream));
         for (size_t p = 0; p < nparts; ++p) {
             const size_t b = begin_of[p], len = begin_of[p + 1] - b;
             ZK_CUDA(cudaStreamWaitEvent(s, g_msm_part_ev[p], 0));
@@ -1645,7 +1664,18 @@ static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stri
             msm_device(c, ds + b, len, 1, t->d, len, &pre, dout, s, part);
         }
         ZK_CUDA(cudaMemcpyAsync(out_xyz, dout, sizeof(G1Jacobian), cudaMemcpyDeviceToHost, s));
+        ZK_CUDA(cudaEventRecord(g_msm_time_ev[3], s));
         ZK_CUDA(cudaStreamSynchronize(s));
+        if (g_msm_pipe_auto) {
+            float ms_copy = 0.f, ms_all = 0.f;
+            if (cudaEventElapsedTime(&ms_copy, g_msm_time_ev[0], g_msm_time_ev[1]) == cudaSuccess &&
+                cudaEventElapsedTime(&ms_all, g_msm_time_ev[2], g_msm_time_ev[3]) == cudaSuccess && ms_copy > 0.f) {
+                const double r = std::min(8.0, std::max(1.0, (double)ms_all / (double)ms_copy));
+                g_msm_pipe_ratio = g_msm_pipe_ratio > 0.0 ? 0.5 * (g_msm_pipe_ratio + r) : r;
+            } else {
+                cudaGetLastError();
+            }
+        }
         return;
     }
     if (n && !resident)
@@ -1720,6 +1750,8 @@ int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n) {
         ZK_REQUIRE(parts <= MSM_MAX_PARTS, "parts out of range");
         g_msm_pipe_parts = parts ? parts : MSM_PIPE_PARTS_DEFAULT;      // 0: the library's defaults
         g_msm_pipe_min_n = parts ? min_n : MSM_PIPE_MIN_N_DEFAULT;
+        g_msm_pipe_auto = parts == 0 && !getenv("B200ZK_MSM_PIPE_GROWTH") && !getenv("B200ZK_MSM_PIPE_PARTS");
+        g_msm_pipe_ratio = 0.0;
     });
 }
 

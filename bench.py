@@ -742,6 +742,13 @@ def run_e2e(args, torch, dist, b200zk, lib, dev, world, rank, k, n, handle, d_sc
                   "b200zk_mirror_enable; b200zk_mirror_invalidate before every step: the host data is new)",
            "rank_order": "odd ranks transform the previous polynomial before committing the next (half the ranks upload while "
                          "half download)" if world > 1 else "commit, then transform"}
+    if world > 1:      # every rank's own call times (the step is the slowest rank's)
+        mine = torch.tensor([1e3 * state["commit_s"] / max(1, state["calls"]), 1e3 * state["transform_s"] / max(1, state["calls"])],
+                            dtype=torch.float64, device=dev)
+        allr = torch.zeros(2 * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        e2e["calls_ms_per_rank"] = {"commit_lagrange": [round(float(x), 2) for x in allr[0::2].tolist()],
+                                    "best_fft": [round(float(x), 2) for x in allr[1::2].tolist()]}
     # same results as the device-resident calls on the same inputs (rank 0, single GPU)
     if rank == 0 and world == 1:
         try:

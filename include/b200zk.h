@@ -385,7 +385,11 @@ int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]);
  * the PCIe upload of range p+1 runs under the sort + accumulation of range p (same group
  * element).  The ranges grow geometrically (each 4x the one before: a short first range so that
  * little has to arrive before the GPU starts, the copy being ~4x faster than the computation it
- * feeds).  parts = 1 disables it; parts = 0 restores the defaults: 3 ranges from 2^22 scalars. */
+ * feeds).  parts = 1 disables it; parts = 0 restores the defaults: from 2^22 scalars, 3 ranges
+ * growing 4x, after which the schedule follows the host link — every piped commit times its
+ * copies and itself and the next one uses growth = 0.9 x (commit time / copy time), in 4 ranges
+ * below growth 3 (several GPUs copying at once share the host's memory bandwidth).  parts > 0
+ * pins the schedule. */
 int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n);
 /* Transfer pipeline of b200zk_ntt / b200zk_intt on one host buffer of at least 2^min_log_n
  * elements: the first pass runs in `chunks` column ranges, each as soon as its rectangle of the
