@@ -607,6 +607,9 @@ __device__ __forceinline__ uint32_t find_key(const uint32_t* __restrict__ start,
     return lo;
 }
 
+// (Tried in round 2: short chunks (L / 4) for the last machine-full of pairs, so that the kernel drains in a quarter
+// of a chunk's time: accumulate 32.10 -> 31.77 ms at 2^24, but the 0.38 M extra open runs cost the keyed levels
+// 0.73 -> 1.08 ms.  Not kept.)
 // (Tried in round 2: the ten products of the mixed addition as calls of one __noinline__ multiplication / squaring
 // body instead of ten inlined copies, to shrink the ~37 KB loop body: 2 950 instead of 4 300 SASS instructions, but
 // 244 MOV + 226 SEL of argument marshalling and 2x the spills: 33.9 ms against 32.1 ms at 2^24.  Not kept.)
