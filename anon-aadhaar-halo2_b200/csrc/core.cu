@@ -108,6 +108,30 @@ __global__ void gen_points_kernel(G1Affine* out, size_t n, uint64_t seed, size_t
     out[i] = r;
 }
 
+template <class F>
+static __global__ void __launch_bounds__(128) field_op_kernel(uint32_t op, const F* __restrict__ a, const F* __restrict__ b,
+                                                              size_t n, F* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const F x = a[i];
+    F r = F::zero();
+    switch (op) {
+        case B200ZK_FIELD_MUL: r = x * b[i]; break;
+        case B200ZK_FIELD_ADD: r = x + b[i]; break;
+        case B200ZK_FIELD_SUB: r = x - b[i]; break;
+        case B200ZK_FIELD_SQR: r = x.sqr(); break;
+        case B200ZK_FIELD_INV: r = x.inverse(); break;
+        case B200ZK_FIELD_NEG: r = x.neg(); break;
+        case B200ZK_FIELD_DBL: r = x.dbl(); break;
+        case B200ZK_FIELD_FROM_MONT: r = x.from_mont(); break;
+        case B200ZK_FIELD_TO_MONT: r = x.to_mont(); break;
+        case B200ZK_FIELD_POW: r = x.pow(b[i].l); break;        // exponent: the 256 bits of b[i] as an integer
+        default: break;
+    }
+    out[i] = r.canon();
+}
+
+
 // ---------------------------------------------------------------- modmul peak probe
 __global__ void __launch_bounds__(256) modmul_peak_kernel(Fq* out, uint32_t iters) {
     // four independent dependency chains per thread
@@ -296,6 +320,32 @@ int b200zk_gen_points_dev(void* d_out, size_t n, uint64_t seed, size_t start) {
         gen_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>((G1Affine*)d_out, n, seed, start, tbl);
         ZK_LAUNCH_CHECK();
         ZK_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+// Element-wise field arithmetic on the device (the known-answer test of SURVEY.md section 7 step 3): out[i] =
+// a[i] op b[i], operands taken as given (any representative in [0, 2p), as values are between kernels), the
+// result canonical.  A diagnostic entry point: the product kernels inline the same Fp<P> operators.
+int b200zk_field_op(uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+    return guarded([&] {
+        ZK_REQUIRE(field <= 1 && op <= B200ZK_FIELD_OP_LAST, "unknown field or operation");
+        ZK_REQUIRE(n == 0 || (a && out), "null argument");
+        const bool binary = op == B200ZK_FIELD_MUL || op == B200ZK_FIELD_ADD || op == B200ZK_FIELD_SUB || op == B200ZK_FIELD_POW;
+        ZK_REQUIRE(n == 0 || !binary || b, "null second operand");
+        if (n == 0) return;
+        ensure_init();
+        Context& c = ctx();
+        cudaStream_t s = c.stream;
+        const size_t bytes = n * 32;
+        char* d = (char*)c.scratch(s).misc.get(3 * bytes);
+        ZK_CUDA(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, s));
+        if (binary) ZK_CUDA(cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyHostToDevice, s));
+        const unsigned blocks = (unsigned)((n + 127) / 128);
+        if (field == 0) field_op_kernel<Fr><<<blocks, 128, 0, s>>>(op, (const Fr*)d, (const Fr*)(d + bytes), n, (Fr*)(d + 2 * bytes));
+        else field_op_kernel<Fq><<<blocks, 128, 0, s>>>(op, (const Fq*)d, (const Fq*)(d + bytes), n, (Fq*)(d + 2 * bytes));
+        ZK_LAUNCH_CHECK();
+        ZK_CUDA(cudaMemcpyAsync(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost, s));
+        ZK_CUDA(cudaStreamSynchronize(s));
     });
 }
 

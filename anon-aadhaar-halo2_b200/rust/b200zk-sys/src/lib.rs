@@ -90,6 +90,7 @@ extern "C" {
     // measurement and test support
     pub fn b200zk_gen_scalars_dev(d_out: *mut c_void, n: usize, seed: u64, start: usize) -> c_int;
     pub fn b200zk_gen_points_dev(d_out: *mut c_void, n: usize, seed: u64, start: usize) -> c_int;
+    pub fn b200zk_field_op(field: u32, op: u32, a: *const u64, b: *const u64, n: usize, out: *mut u64) -> c_int;
     pub fn b200zk_modmul_peak(iters: u32, modmul_per_s_out: *mut f64) -> c_int;
     pub fn b200zk_msm_profile(enable: c_int) -> c_int;
     pub fn b200zk_msm_tune(max_chunk: u32, max_seglen: u32, force_window_bits: u32) -> c_int;

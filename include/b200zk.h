@@ -368,6 +368,19 @@ int b200zk_gen_scalars_dev(void* d_out, size_t n, uint64_t seed, size_t start);
 int b200zk_gen_points_dev(void* d_out, size_t n, uint64_t seed, size_t start);
 
 /* ---- measurement support ------------------------------------------------------------ */
+/* Element-wise field arithmetic on the device: out[i] = a[i] op b[i] for n elements of Fr (field = 0) or
+ * Fq (field = 1), 4 limbs each.  Operands are taken as given — any representative in [0, 2p), Montgomery
+ * form for the arithmetic operations — and the result is the canonical representative.  The known-answer
+ * hook for halo2curves 0.3.1 `bn256::{Fr, Fq}` (Mul / Add / Sub / square / invert / neg / double /
+ * from_repr / to_repr / pow; [DEP] halo2curves src/bn256/{fr,fq}.rs, reference Cargo.lock:484-486): the
+ * kernels of this library inline the same operators.  `b` may be null for the unary operations;
+ * B200ZK_FIELD_INV maps 0 to 0; B200ZK_FIELD_POW raises a[i] to the 256-bit integer held in b[i]. */
+enum {
+    B200ZK_FIELD_MUL = 0, B200ZK_FIELD_ADD = 1, B200ZK_FIELD_SUB = 2, B200ZK_FIELD_SQR = 3, B200ZK_FIELD_INV = 4,
+    B200ZK_FIELD_NEG = 5, B200ZK_FIELD_DBL = 6, B200ZK_FIELD_FROM_MONT = 7, B200ZK_FIELD_TO_MONT = 8,
+    B200ZK_FIELD_POW = 9, B200ZK_FIELD_OP_LAST = 9
+};
+int b200zk_field_op(uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
 /* Register-resident Fq multiply chain on every SM; returns field multiplications / s.
  * This is the measured denominator of the MSM integer-pipe roofline. */
 int b200zk_modmul_peak(uint32_t iters, double* modmul_per_s_out);
