@@ -152,14 +152,21 @@ def test_commit_at_benchmark_size_matches_known_discrete_logs(zk):
     got = d_out.cpu().numpy().view(np.uint64)
     plain = np.zeros(12, dtype=np.uint64)
     zk.check(lib.b200zk_msm_g1_dev(C.c_void_p(ds.data_ptr()), C.c_void_p(db.data_ptr()), n, C.c_void_p(plain.ctypes.data), None))
-    zk.check(lib.b200zk_bases_evict(h.value))
     s = ds.cpu().numpy().view(np.uint64).reshape(n, 4)
+    # the same commit through the host-pointer call (what bench.py's e2e leg times): the upload pipeline's default
+    # schedule (three point ranges growing 4x), then the schedule it derives from the first call's copy / commit times
+    piped = [np.zeros(12, dtype=np.uint64) for _ in range(3)]
+    with zk.pinned(s):
+        for out in piped:
+            zk.check(lib.b200zk_msm_g1_registered(h.value, C.c_void_p(s.ctypes.data), n, C.c_void_p(out.ctypes.data)))
+    zk.check(lib.b200zk_bases_evict(h.value))
     with np.errstate(over="ignore"):
         t = bn._splitmix64_np(np.uint64(((0xBA5E0000 + k) << 32) & ((1 << 64) - 1)) + np.arange(n, dtype=np.uint64)) | np.uint64(1)
     scalar = _dot_mod_r(s, t) % bn.R * pow(1 << 256, -1, bn.R) % bn.R       # scalars are Montgomery representatives
     want = bn.g1_mul(bn.G1_GEN, scalar)
     assert jac_affine(got) == want
     assert jac_affine(plain) == want
+    assert [jac_affine(o) for o in piped] == [want] * 3
 
 
 @pytest.mark.parametrize("precompute", [True, False])
