@@ -850,10 +850,11 @@ def run_e2e(args, torch, dist, b200zk, lib, dev, world, rank, k, n, handle, d_sc
 
 
 def run_sharded_ntt(torch, dist, lib, b200zk, world: int, rank: int, dev, k: int, single_ms: float):
-    """One 2^k best_fft over all ranks (strong scaling of a single transform): local column
-    NTTs, twiddle pass that stores straight into the peers' row buffers over NVLink (falls back
-    to a NCCL all-to-all when peer mappings are unavailable), local row NTTs."""
+    """One 2^k best_fft over all ranks (strong scaling of a single transform): the transform's first pass on the
+    rank's columns stores straight into the peers' row buffers over NVLink (falls back to a NCCL all-to-all when
+    peer mappings are unavailable), then the local row transforms."""
     from b200zk import sharding
+    from b200zk.api import _ptr as _ptr_np
     vp = lambda t: C.c_void_p(t.data_ptr())
     n = 1 << k
     log_n1 = sharding.four_step_split(k, world)
@@ -865,8 +866,22 @@ def run_sharded_ntt(torch, dist, lib, b200zk, world: int, rank: int, dev, k: int
     omega = omega_for(k)
     reps = 5
     xs = [x0.clone() for _ in range(reps + 1)]
-    sharding.sharded_best_fft(xs[reps], k, omega, ops, world, rank)
+    rows_out = sharding.sharded_best_fft(xs[reps], k, omega, ops, world, rank)
     torch.cuda.synchronize()
+    # parity, live: the natural-order vector whose column blocks are the ranks' slabs, transformed on this GPU alone,
+    # must hold this rank's rows (row i1, position i2  <->  A[i1 + n1 i2])
+    full = torch.empty(n * 4, dtype=torch.int64, device=dev)
+    slab = torch.empty(m * n1 * 4, dtype=torch.int64, device=dev)
+    for r in range(world):
+        b200zk.check(lib.b200zk_gen_scalars_dev(vp(slab), m * n1, SEED_S + k, r * m * n1))
+        full.view(n1, n2, 4)[:, r * m:(r + 1) * m].copy_(slab.view(n1, m, 4))
+    b200zk.check(lib.b200zk_ntt_dev(vp(full), n, 1, k, _ptr_np(fr_limbs(omega)), None, None))
+    torch.cuda.synchronize()
+    r0, nrows = rank * (n1 // world), n1 // world
+    want = full.view(n2, n1, 4)[:, r0:r0 + nrows].permute(1, 0, 2).contiguous().view(-1)
+    same = torch.tensor([1 if torch.equal(rows_out.view(-1), want) else 0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    del full, slab, want
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -878,6 +893,7 @@ def run_sharded_ntt(torch, dist, lib, b200zk, world: int, rank: int, dev, k: int
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     return {"k": k, "ms": ms, "melem_per_s": n / ms / 1e3, "exchange": ops.mode,
+            "same_transform_as_single_gpu": bool(same.item()), "split": f"2^{log_n1} x 2^{k - log_n1}",
             "speedup_vs_one_gpu": single_ms / ms, "exchange_bytes_per_rank": (world - 1) * n * 32 // (world * world),
             "layout": "rank r holds columns j2 in [r m, (r+1) m) in, rows i1 in [r n1/N, (r+1) n1/N) out"}
 
