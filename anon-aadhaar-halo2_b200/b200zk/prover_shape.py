@@ -503,7 +503,8 @@ class ProverHotPath:
         world = self.world
         b, e = self.commit_ranges[self.rank]
         mine = torch.tensor([t["commit_own_columns"] / max(1, e - b) if e > b else 0.0,
-                             t["coset_ntt_and_quotient_own_cosets"] + t.get("finish_h_on_rank0", 0.0)], dtype=torch.float64, device="cuda")
+                             t["all_gather_coefficient_columns"] + t["coset_ntt_and_quotient_own_cosets"] + t.get("finish_h_on_rank0", 0.0)],
+                            dtype=torch.float64, device="cuda")
         allv = torch.zeros(2 * world, dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_gather_into_tensor(allv, mine)
@@ -521,7 +522,8 @@ class ProverHotPath:
         coset path on one GPU.  `torch` supplies the NCCL collectives and the device copies around library-owned memory.
 
         Schedule: (1) every rank takes its even share of the Lagrange columns to coefficient form (a copy: the Lagrange
-        columns are still to be committed) and the coefficient columns are all-gathered; (2) the ranks that own cosets
+        columns are still to be committed) and the coefficient columns are all-gathered — only the coset owners wait for
+        that; (2) the ranks that own cosets
         of the extended domain extend and evaluate them; the all-gather of the evaluated cosets is issued
         asynchronously, so ranks without cosets do not wait for it; (3) every rank commits its load-weighted share of
         the Lagrange columns; (4) rank 0, which has the fewest columns, finishes h(X) (interleave, divide,
@@ -530,8 +532,9 @@ class ProverHotPath:
         world, rank = self.world, self.rank
         t, marks = {}, [time.perf_counter()]
 
-        def mark(name):
-            self.sync()
+        def mark(name, sync=True):
+            if sync:
+                self.sync()
             marks.append(time.perf_counter())
             t[name] = 1e3 * (marks[-1] - marks[-2])
 
@@ -548,12 +551,19 @@ class ProverHotPath:
             self.sync()
             check(lib.b200zk_ntt_dev(C.c_void_p(self.coef_mine.ptr), n, e - b, d.k, _ptr(d.omega_inv), _ptr(d.ifft_divisor), None))
         mark("lagrange_to_coeff_own_columns")
+        coef_work = None
         if world > 1:
-            dist.all_gather_into_tensor(self._torch_view(torch, self.coef_all, 0, world * self.maxc * n),
-                                        self._torch_view(torch, self.coef_mine, 0, self.maxc * n))
+            # only the ranks that own a coset read the gathered coefficient columns: the others take part in the
+            # collective but go straight on to their commitments (the copy engines and a few SMs do the gathering)
+            coef_work = dist.all_gather_into_tensor(self._torch_view(torch, self.coef_all, 0, world * self.maxc * n),
+                                                    self._torch_view(torch, self.coef_mine, 0, self.maxc * n), async_op=True)
+            if self.my_cosets:
+                coef_work.wait()
+                coef_work = None
         else:
             self._torch_view(torch, self.coef_all, 0, self.maxc * n).copy_(self._torch_view(torch, self.coef_mine, 0, self.maxc * n))
-        mark("all_gather_coefficient_columns")
+        # (a device-wide synchronisation would wait for the gathering: a rank without cosets has nothing to wait for here)
+        mark("all_gather_coefficient_columns", sync=bool(self.my_cosets) or world == 1)
         # ---- (2) own cosets of the extended domain
         env_scal = self.scalars
         zeta_delta = fr_limbs(FR_DELTA)
@@ -599,7 +609,7 @@ class ProverHotPath:
                                                  col(lk0 + 2 * j).handle, col(lk0 + 2 * j + 1).handle, l0.handle,
                                                  l_last.handle, l_active.handle))
             values.free()
-        mark("coset_ntt_and_quotient_own_cosets")
+        mark("coset_ntt_and_quotient_own_cosets", sync=bool(self.my_cosets) or world == 1)
         # the evaluated cosets travel to rank 0 while everybody commits: asynchronous, so a rank without cosets (it
         # arrives here at once) does not wait for the ranks that have some
         h_work = None
@@ -612,6 +622,8 @@ class ProverHotPath:
             self._commit(self.lag_pad.ptr + cb * n * 32, ce - cb, cb)
         mark("commit_own_columns")
         # ---- (4) h(X) on rank 0
+        if coef_work is not None:
+            coef_work.wait()
         if h_work is not None:
             h_work.wait()
         mark("gather_h_cosets")
