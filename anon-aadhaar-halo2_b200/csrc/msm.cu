@@ -1057,7 +1057,9 @@ enum MsmStage { MSM_ST_HIST = 0, MSM_ST_SCAN, MSM_ST_SCATTER, MSM_ST_SYNC, MSM_S
 struct MsmInfo { uint64_t n; uint32_t c, nwin, npairs, chunk; };
 static bool g_msm_profile = false;
 static uint32_t g_msm_max_chunk = 128;   // tunable (b200zk_msm_tune)
-static uint32_t g_msm_max_seglen = 64;    // measured: 104 -> 64 takes the 242-column reduce from 3.5 to 3.1 ms
+static bool g_msm_seg_pinned = getenv("B200ZK_MSM_SEG_DIV") || getenv("B200ZK_MSM_MAX_SEGLEN");   // experiments
+static uint32_t g_msm_seg_div = getenv("B200ZK_MSM_SEG_DIV") ? (uint32_t)atoi(getenv("B200ZK_MSM_SEG_DIV")) : 256u;   // segments per SM aimed at
+static uint32_t g_msm_max_seglen = getenv("B200ZK_MSM_MAX_SEGLEN") ? (uint32_t)atoi(getenv("B200ZK_MSM_MAX_SEGLEN")) : 64;    // measured: 104 -> 64 takes the 242-column reduce from 3.5 to 3.1 ms
 static uint32_t g_msm_force_c = 0;
 // scatter sub-range bits; B200ZK_MSM_SUB_BITS overrides the automatic choice (experiments only)
 // upload pipeline of b200zk_msm_g1_registered (one large host-side commit): number of point
@@ -1294,7 +1296,14 @@ static void msm_device(Context& c, const Fr* d_scalars, size_t scalar_stride, si
     const uint32_t scan_blocks = (uint32_t)((nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK);
     // segment length of the bucket reduction: enough segments to fill the machine, short
     // enough that 2 * seglen dependent additions stay cheap
-    uint32_t seglen = (uint32_t)std::min<uint64_t>(g_msm_max_seglen, std::max<uint64_t>(4, nkeys / ((uint64_t)c.sm_count * 256)));
+    // Measured on B200 (scratch/r2_seg_sweep.sh, batches of 2^15-point columns, 2^14 buckets each; reduce + sum of the
+    // segment partials): below 2^20 buckets ~96 segments per SM — few enough for the 4-lane cooperative kernel, at most
+    // 128 buckets each — beat 256 per SM (8 columns 0.54 -> 0.37 ms, 16: 0.65 -> 0.49, 32: 0.84 -> 0.74); from 2^20
+    // buckets up one lane per segment of <= 64 buckets wins (64 columns 1.18 against 1.27 ms, 2^21 buckets 1.92 / 2.02)
+    const bool mid = nkeys < (1u << 20) && !g_msm_seg_pinned;
+    const uint32_t seg_div = mid ? 96u : g_msm_seg_div;
+    const uint32_t max_seglen = mid ? std::max<uint32_t>(g_msm_max_seglen, 128u) : g_msm_max_seglen;
+    uint32_t seglen = (uint32_t)std::min<uint64_t>(max_seglen, std::max<uint64_t>(4, nkeys / ((uint64_t)c.sm_count * seg_div)));
     if (seglen > nb) seglen = nb;
     const uint32_t segs_per_group = (nb + seglen - 1) / seglen;
     const size_t red_entries = (size_t)segs_per_group * groups;
@@ -1744,6 +1753,7 @@ int b200zk_msm_tune(uint32_t max_chunk, uint32_t max_seglen, uint32_t force_wind
         ZK_REQUIRE(force_window_bits == 0 || (force_window_bits >= 4 && force_window_bits <= 23), "window bits out of range");
         g_msm_max_chunk = max_chunk;
         g_msm_max_seglen = max_seglen;
+        g_msm_seg_pinned = max_seglen != 64;      // a caller-chosen segment length holds at every size
         g_msm_force_c = force_window_bits;
     });
 }
