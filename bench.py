@@ -666,9 +666,8 @@ def run_e2e(args, torch, dist, b200zk, lib, dev, world, rank, k, n, handle, d_sc
     in HBM, runs there and writes the result back.  Every step starts from host data the library has not seen
     (b200zk_mirror_invalidate: new witness values), so a step moves 2^k * 32 B up and 2^k * 32 B + 96 B down.
     `separate_buffers`: round 1's definition (two unrelated host buffers, no mirrors: 2 * 2^k * 32 B up), kept for
-    comparison.  With N > 1 the odd ranks run one polynomial behind (transform of the previous polynomial, then the
-    commit of the next) so that half of the ranks upload while the other half downloads, and the one-point gather + fold
-    sits at the end of the step."""
+    comparison.  With N > 1 the ranks run free (staggered starts, the one-point gather + fold one step behind: see
+    below); the in-step schedule of the first half of round 2 is timed beside it (`lockstep`)."""
     from b200zk.api import _ptr
     vp = lambda t: C.c_void_p(t.data_ptr())
     out = np.zeros(12, dtype=np.uint64)
@@ -728,10 +727,82 @@ def run_e2e(args, torch, dist, b200zk, lib, dev, world, rank, k, n, handle, d_sc
         gather_fold()
 
     warm = max(2, min(args.warmup, 3))
-    for _ in range(warm):
-        shared_step()
-    state.update(commit_s=0.0, transform_s=0.0, calls=0)
-    dt = timed(shared_step, args.steps, 0)
+    if world == 1:
+        for _ in range(warm):
+            shared_step()
+        state.update(commit_s=0.0, transform_s=0.0, calls=0)
+        dt = timed(shared_step, args.steps, 0)
+        order = "commit, then transform"
+        lockstep = None
+    else:
+        # (a) round 2's first schedule, kept for comparison: every rank in step (the gather + fold closes every step),
+        # odd ranks one polynomial behind so that half of them upload while the other half downloads
+        for _ in range(warm):
+            shared_step()
+        steps_a = max(2, min(args.steps, 5))
+        dt_a = timed(shared_step, steps_a, 0)
+        lockstep = {"value": world * n * steps_a / dt_a / 1e6, "ms_per_step": 1e3 * dt_a / steps_a, "steps": steps_a,
+                    "what": "all ranks in step: gather + fold of the commitments at the end of every step, odd ranks one "
+                            "polynomial behind"}
+        # (b) headline: the ranks run free.  The commitments of a step are gathered asynchronously and folded one step
+        # later (nothing in a step waits for another rank), and the ranks' starts are staggered (below), so that the eight
+        # 0.5 GiB downloads — what the host link cannot take all at once (`pcie_concurrent`) — follow one another
+        # instead of coinciding.  Every copy, every gather and every fold is still inside the timed region.
+        lag = False
+        gbuf = [torch.zeros(world * 12, dtype=torch.int64, device=dev) for _ in range(2)]
+        dbuf = [torch.zeros(12, dtype=torch.int64, device=dev) for _ in range(2)]
+        pending = []
+
+        def fold_all_but(keep):
+            while len(pending) > keep:
+                w, i = pending.pop(0)
+                w.wait()
+                if rank == 0:
+                    pts = gbuf[i].cpu().numpy().view(np.uint64).reshape(world, 12)
+                    b200zk.g1_sum(np.ascontiguousarray(pts))
+
+        behind = [False]       # odd ranks: transform the polynomial committed one step ago, then commit the next
+
+        def free_step():
+            cur, prev = polys[state["i"] & 1], polys[(state["i"] + 1) & 1]
+            state["i"] += 1
+            b200zk.check(lib.b200zk_mirror_invalidate(vp(cur), 0))
+            if behind[0]:
+                transform(prev)
+                commit(cur)
+            else:
+                commit(cur)
+                transform(cur)
+            i = state["i"] & 1
+            dbuf[i].copy_(torch.from_numpy(out.view(np.int64)))
+            pending.append((dist.all_gather_into_tensor(gbuf[i], dbuf[i], async_op=True), i))
+            fold_all_but(1)
+
+        t0 = time.perf_counter()
+        for _ in range(2):
+            free_step()
+        fold_all_but(0)
+        torch.cuda.synchronize()
+        est = torch.tensor([(time.perf_counter() - t0) / 2], dtype=torch.float64, device=dev)
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+        # Download windows (the last ~10 ms of a transform call) spread over the step at the least cost in idle starts:
+        # the odd ranks run one polynomial behind — their window falls a quarter of a step after their neighbour's at no
+        # cost — and every further pair of ranks starts 8 ms (or 1/N of a step, if shorter) after the pair before
+        behind[0] = rank % 2 == 1
+        offset = min(float(est.item()) / world, 0.008) * (rank // 2)
+        state.update(commit_s=0.0, transform_s=0.0, calls=0)
+        barrier()
+        t0 = time.perf_counter()
+        time.sleep(offset)
+        for _ in range(args.steps):
+            free_step()
+        fold_all_but(0)
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        order = ("ranks run free: odd ranks one polynomial behind, every further pair of ranks starts 8 ms later, the commitments "
+                 "of a step are gathered asynchronously and folded one step later; all of it inside the timed region")
     e2e = {"value": world * n * args.steps / dt / 1e6, "unit": UNIT,
            "h2d_bytes_per_step": world * n * 32, "d2h_bytes_per_step": world * (n * 32 + 96),
            "ms_per_step": 1e3 * dt / args.steps,
@@ -740,8 +811,9 @@ def run_e2e(args, torch, dist, b200zk, lib, dev, world, rank, k, n, handle, d_sc
            "api": "b200zk_msm_g1_registered (ParamsKZG::commit_lagrange: the polynomial from page-locked host memory, SRS "
                   "resident) + b200zk_ntt (best_fft in place on the same host polynomial, found in its device mirror: "
                   "b200zk_mirror_enable; b200zk_mirror_invalidate before every step: the host data is new)",
-           "rank_order": "odd ranks transform the previous polynomial before committing the next (half the ranks upload while "
-                         "half download)" if world > 1 else "commit, then transform"}
+           "rank_order": order}
+    if lockstep is not None:
+        e2e["lockstep"] = lockstep
     if world > 1:      # every rank's own call times (the step is the slowest rank's)
         mine = torch.tensor([1e3 * state["commit_s"] / max(1, state["calls"]), 1e3 * state["transform_s"] / max(1, state["calls"])],
                             dtype=torch.float64, device=dev)
