@@ -112,6 +112,7 @@ def load() -> C.CDLL:
         "b200zk_host_free": ([vp], C.c_int),
         "b200zk_msm_tune": ([u32, u32, u32], C.c_int),
         "b200zk_msm_upload_pipeline": ([u32, sz], C.c_int),
+        "b200zk_msm_upload_ranges": ([sz, u32, C.c_double, vp, vp], C.c_int),
         "b200zk_field_op": ([u32, u32, vp, vp, sz, vp], C.c_int),
         "b200zk_ntt_transfer_pipeline": ([u32, u32], C.c_int),
         "b200zk_ntt_tune": ([u32], C.c_int),

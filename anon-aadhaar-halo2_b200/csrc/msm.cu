@@ -1600,6 +1600,25 @@ int b200zk_bases_evict(uint64_t handle) {
     });
 }
 
+// Point ranges of the upload pipeline: up to `parts` consecutive ranges of [0, n) whose lengths grow by `growth` from
+// one to the next (1: equal), every boundary but the last a multiple of 256 points.  begin_of[0 .. count] on return.
+static size_t msm_upload_ranges(size_t n, size_t parts, double growth, size_t* begin_of) {
+    parts = std::max<size_t>(1, std::min<size_t>(parts, MSM_MAX_PARTS));
+    const double g = std::max(1.0, growth);
+    double sum = 0, w = 1;
+    for (size_t p = 0; p < parts; ++p, w *= g) sum += w;
+    size_t count = 0, b = 0;
+    w = 1;
+    for (size_t p = 0; p < parts && b < n; ++p, w *= g) {
+        size_t len = p + 1 == parts ? n - b : align_up((size_t)((double)n * (w / sum)) + 1, 256);
+        len = std::min(len, n - b);
+        begin_of[count++] = b;
+        b += len;
+    }
+    begin_of[count] = n;
+    return count;
+}
+
 static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stride, size_t count, size_t n,
                            uint64_t* out_xyz) {
     ZK_REQUIRE(out_xyz && (n == 0 || scalars), "null argument");
@@ -1640,21 +1659,7 @@ static void msm_registered(uint64_t handle, const uint64_t* scalars, size_t stri
         }
         // range lengths in geometric progression (growth 1: equal ranges), multiples of 256 points
         size_t begin_of[MSM_MAX_PARTS + 1];
-        size_t nparts = 0;
-        {
-            const double g = growth;
-            double sum = 0, w = 1;
-            for (size_t p = 0; p < parts; ++p, w *= g) sum += w;
-            size_t b = 0;
-            w = 1;
-            for (size_t p = 0; p < parts && b < n; ++p, w *= g) {
-                size_t len = p + 1 == parts ? n - b : align_up((size_t)((double)n * (w / sum)) + 1, 256);
-                len = std::min(len, n - b);
-                begin_of[nparts++] = b;
-                b += len;
-            }
-            begin_of[nparts] = n;
-        }
+        const size_t nparts = msm_upload_ranges(n, parts, growth, begin_of);
         size_t longest = 0;
         for (size_t p = 0; p < nparts; ++p) longest = std::max(longest, begin_of[p + 1] - begin_of[p]);
         ZK_CUDA(cudaEventRecord(g_msm_part_ev[MSM_MAX_PARTS], s));   // earlier users of the staging buffer
@@ -1765,6 +1770,14 @@ int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n) {
         g_msm_pipe_min_n = parts ? min_n : MSM_PIPE_MIN_N_DEFAULT;
         g_msm_pipe_auto = parts == 0 && !getenv("B200ZK_MSM_PIPE_GROWTH") && !getenv("B200ZK_MSM_PIPE_PARTS");
         g_msm_pipe_ratio = 0.0;
+    });
+}
+
+int b200zk_msm_upload_ranges(size_t n, uint32_t parts, double growth, size_t* begin_out, uint32_t* count_out) {
+    return guarded([&] {
+        ZK_REQUIRE(begin_out && count_out, "null argument");
+        ZK_REQUIRE(parts >= 1 && parts <= MSM_MAX_PARTS, "parts out of range");
+        *count_out = (uint32_t)msm_upload_ranges(n, parts, growth, begin_out);
     });
 }
 

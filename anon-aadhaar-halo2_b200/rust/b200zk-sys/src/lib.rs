@@ -96,6 +96,7 @@ extern "C" {
     pub fn b200zk_msm_tune(max_chunk: u32, max_seglen: u32, force_window_bits: u32) -> c_int;
     pub fn b200zk_msm_last_stages(ms_out: *mut f32, capacity: c_int, info_out: *mut u64) -> c_int;
     pub fn b200zk_msm_upload_pipeline(parts: u32, min_n: usize) -> c_int;
+    pub fn b200zk_msm_upload_ranges(n: usize, parts: u32, growth: f64, begin_out: *mut usize, count_out: *mut u32) -> c_int;
     pub fn b200zk_ntt_transfer_pipeline(chunks: u32, min_log_n: u32) -> c_int;
     pub fn b200zk_ntt_tune(direct_twiddle_max_log_n: u32) -> c_int;
     pub fn b200zk_kernel_launches() -> u64;

@@ -404,6 +404,10 @@ int b200zk_msm_last_stages(float* ms_out, int capacity, uint64_t info_out[5]);
  * below growth 3 (several GPUs copying at once share the host's memory bandwidth).  parts > 0
  * pins the schedule. */
 int b200zk_msm_upload_pipeline(uint32_t parts, size_t min_n);
+/* The point ranges that pipeline uses for n scalars, `parts` ranges and a growth factor (pure host function, no
+ * device needed): begin_out[0 .. *count_out] with begin_out[0] = 0 and begin_out[*count_out] = n; begin_out must
+ * hold parts + 1 entries; parts in 1..16.  Fewer ranges than asked for come back when n is small. */
+int b200zk_msm_upload_ranges(size_t n, uint32_t parts, double growth, size_t* begin_out, uint32_t* count_out);
 /* Transfer pipeline of b200zk_ntt / b200zk_intt on one host buffer of at least 2^min_log_n
  * elements: the first pass runs in `chunks` column ranges, each as soon as its rectangle of the
  * input has arrived, and the last pass likewise, each rectangle of the output leaving while the

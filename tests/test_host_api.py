@@ -38,6 +38,47 @@ def test_length_assertions_mirror_upstream():
         d.extended_to_coeff(np.zeros((8, 4), dtype=np.uint64))
 
 
+def test_upload_pipeline_ranges():
+    """b200zk_msm_upload_ranges (pure host code, no device): the point ranges a piped commit is fed in cover [0, n)
+    exactly once, every inner boundary is a multiple of 256 points, lengths grow by the factor asked for, and small n
+    yields fewer ranges instead of empty ones."""
+    import ctypes as C
+
+    import b200zk
+
+    lib = b200zk.load()
+
+    def ranges(n, parts, growth):
+        begin = (C.c_size_t * (parts + 1))()
+        count = C.c_uint32(0)
+        b200zk.check(lib.b200zk_msm_upload_ranges(n, parts, growth, begin, C.byref(count)))
+        return [int(begin[i]) for i in range(count.value + 1)]
+
+    for n in (0, 1, 255, 256, 257, 300, 4096, 5000, (1 << 14) + 77, 1 << 16, (1 << 22) - 3, 1 << 24, (1 << 26) + 1):
+        for parts in (1, 2, 3, 4, 5, 16):
+            for growth in (1.0, 1.8, 4.0, 0.5):
+                b = ranges(n, parts, growth)
+                assert b[0] == 0 and b[-1] == n and len(b) - 1 <= parts
+                assert all(x < y for x, y in zip(b, b[1:])) or n == 0
+                assert all(x % 256 == 0 for x in b[:-1])
+                if n == 0:
+                    assert b == [0]
+    # the default schedule at the benchmark size: 1/21, 4/21, 16/21 of 2^24 points
+    b = ranges(1 << 24, 3, 4.0)
+    lens = [y - x for x, y in zip(b, b[1:])]
+    assert len(lens) == 3 and abs(lens[0] - (1 << 24) / 21) <= 256 and abs(lens[1] - 4 * (1 << 24) / 21) <= 256
+    assert 3.9 < lens[1] / lens[0] < 4.1 and 3.9 < lens[2] / lens[1] < 4.1
+    # equal ranges with growth 1
+    b = ranges(1 << 22, 4, 1.0)
+    lens = [y - x for x, y in zip(b, b[1:])]
+    assert len(lens) == 4 and max(lens) - min(lens) <= 1024
+    # parts out of range
+    begin = (C.c_size_t * 18)()
+    count = C.c_uint32(0)
+    assert lib.b200zk_msm_upload_ranges(100, 0, 1.0, begin, C.byref(count)) != 0
+    assert lib.b200zk_msm_upload_ranges(100, 17, 1.0, begin, C.byref(count)) != 0
+
+
 @pytest.mark.gpu
 def test_page_locked_host_buffers(zk):
     """b200zk_host_register / b200zk_host_alloc: same results from pageable, registered and
